@@ -1,0 +1,165 @@
+/* svirl_b200 -- C ABI of the B200-native TDGL / CG hot path.
+ *
+ * This shared library replaces the pyCUDA layer of microsoft/svirl
+ * (svirl/cuda/*.h kernels, svirl/parallel/{startup,reduction,utils}.py,
+ * svirl/storage/arrays.py device side).  Plain pointers and sizes only: the
+ * caller owns host (numpy) buffers, the library owns device memory.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure;
+ *     svl_last_error() returns the message of the last failure on this thread.
+ *   - not thread-safe per context; one context per process/GPU is the intended use.
+ *   - host arrays are in the reference's flat device layout (x fastest):
+ *       nodes  n = i + Nx*j              (svirl/cuda/common.h:75-81)
+ *       edges  a: i + (Nx-1)*j ; b: Na + i + Nx*j, Na=(Nx-1)*Ny  (svirl/cuda/td.h:91-100)
+ *       cells  i + (Nx-1)*j
+ *     device storage is pitched planes; conversion happens in h2d/d2h.
+ *   - `real` scalars are passed as double and rounded to the context dtype inside.
+ *   - a NULL svl_buf* means "absent" exactly where the reference passes np.uintp(0).
+ */
+#ifndef SVIRL_B200_H
+#define SVIRL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct svl_ctx svl_ctx;
+typedef struct svl_buf svl_buf;
+
+/* buffer kinds */
+enum {
+    SVL_NODE_C = 0, /* complex on nodes, Nx*Ny            (psi, jacobian_psi, directions)   */
+    SVL_NODE_R = 1, /* real on nodes                      (spatial linear coefficient)      */
+    SVL_EDGE   = 2, /* real on edges, a then b, Na+Nb     (vector potential and friends)    */
+    SVL_CELL_R = 3, /* real on cells (Nx-1)*(Ny-1)        (magnetic field)                  */
+    SVL_CELL_B = 4, /* 1 byte on cells                    (material tiling)                 */
+    SVL_FLAT   = 5  /* contiguous array of n elements of elem_size bytes                    */
+};
+
+const char *svl_last_error(void);
+int svl_version(void);
+
+/* ---- lifecycle: replaces Startup.__init__/__del__ (svirl/parallel/startup.py:17-93).
+ * dtype_bytes: 4 (float/complex64) or 8 (double/complex128).
+ * dx, dy: as double(str(np.floatXX(dx))) -- the reference embeds the decimal repr and folds
+ * 1/(dx*dx) in double (startup.py:54-60, td.h:34-35).
+ * Slab decomposition (multi-GPU, new): this context owns node rows [j0, j1) of the global
+ * Ny rows; single GPU: j0 = 0, j1 = Ny. */
+int svl_create(svl_ctx **out, int device_id, int Nx, int Ny, double dx, double dy, int dtype_bytes,
+               int j0, int j1);
+int svl_destroy(svl_ctx *ctx);
+int svl_synchronize(svl_ctx *ctx);
+/* knobs: "psi_kernel" (0 = plain per-node, 1 = temporally blocked streaming), "psi_k" (sweeps
+ * fused per launch), "tma" (0/1), "graphs" (0/1) */
+int svl_set_option(svl_ctx *ctx, const char *name, int value);
+int svl_get_stat(svl_ctx *ctx, const char *name, double *value);
+
+/* ---- buffers: replaces pycuda.gpuarray + cuda.memcpy_* (svirl/storage/arrays.py:520-587,
+ * svirl/parallel/utils.py:21-27).  n is only used for SVL_FLAT. */
+int svl_alloc(svl_ctx *ctx, int kind, size_t n, int elem_size, svl_buf **out);
+int svl_free(svl_ctx *ctx, svl_buf *buf);
+int svl_h2d(svl_ctx *ctx, svl_buf *dst, const void *src);   /* full array, reference flat layout */
+int svl_d2h(svl_ctx *ctx, void *dst, const svl_buf *src);
+int svl_d2d(svl_ctx *ctx, svl_buf *dst, const svl_buf *src);
+int svl_fill_zero(svl_ctx *ctx, svl_buf *buf);
+int svl_swap(svl_ctx *ctx, svl_buf *x, svl_buf *y);         /* swap storage of two same-kind buffers */
+size_t svl_buf_size(const svl_buf *buf);                    /* elements in the flat layout */
+/* row-slab transfers for fields too large for one host array (rows [r0, r1) of the plane;
+ * part = 0 for nodes/cells/a, 1 for b) */
+int svl_h2d_rows(svl_ctx *ctx, svl_buf *dst, int part, int r0, int r1, const void *src);
+int svl_d2h_rows(svl_ctx *ctx, void *dst, const svl_buf *src, int part, int r0, int r1);
+
+/* material tiling -> per-node flag plane (bits mm,mp,pm,pp: svirl/cuda/td.h:48-57).
+ * mt == NULL: no tiling (all in-range cells are material). Must be called once before solving
+ * and again whenever the tiling changes (mesh/grid.py:103-120). */
+int svl_set_material(svl_ctx *ctx, const svl_buf *mt);
+
+/* ---- TDGL (hot path 1) -------------------------------------------------------------- */
+
+/* One Jacobi sweep: iterate_order_parameter_jacobi_step (svirl/cuda/td.h:5-133).
+ * r_out = max over all nodes of max(|dRe|,|dIm|). */
+int svl_td_psi_sweep(svl_ctx *ctx, double dt, double eps, const svl_buf *eps_field, const svl_buf *ab,
+                     svl_buf *psi_rhs, const svl_buf *psi, svl_buf *psi_next, double langevin_c,
+                     uint32_t jstep, uint32_t rand_t, double *r_out);
+/* One Jacobi sweep: iterate_vector_potential_jacobi_step (svirl/cuda/td.h:311-463).
+ * ab_phase is the kernel's `abi_ab_rhs` argument and may alias ab_next (quirk Q1). */
+int svl_td_a_sweep(svl_ctx *ctx, double dt, double kappa2, double rho, double H, const svl_buf *psi,
+                   const svl_buf *ab_phase, svl_buf *ab_rhs, const svl_buf *ab, svl_buf *ab_next,
+                   double langevin_c, uint32_t jstep, uint32_t rand_t, double *r_out);
+
+/* Whole psi-solve (svirl/solvers/td.py:157-218): <=1024 sweeps, stops after the first sweep
+ * with r < stop_eps (exact reference rule int32(real(1e4 r/eps)) < 10000); psi is updated in
+ * place (storage rotation, no copy).  sweeps_out = executed (= reference) sweep count. */
+int svl_td_psi_solve(svl_ctx *ctx, double dt, double eps, const svl_buf *eps_field, const svl_buf *ab,
+                     svl_buf *psi, double langevin_c, uint32_t rand_t, double stop_eps, int *sweeps_out);
+/* Whole A-solve (svirl/solvers/td.py:252-325) including the link-phase aliasing quirk Q1. */
+int svl_td_a_solve(svl_ctx *ctx, double dt, double kappa2, double rho, double H, const svl_buf *psi,
+                   svl_buf *ab, double langevin_c, uint32_t rand_t, double stop_eps, int *sweeps_out);
+/* Nt time steps of [psi-solve; A-solve if solveA] (svirl/solvers/td.py:342-367); rand_t is
+ * incremented after every solve and returned.  sweeps[0..1] accumulate psi / A sweep counts. */
+int svl_td_run(svl_ctx *ctx, int Nt, double dt, int solveA, double eps, const svl_buf *eps_field,
+               double kappa2, double rho, double H, svl_buf *psi, svl_buf *ab, double langevin_psi,
+               double langevin_A, uint32_t *rand_t, double stop_psi, double stop_A, long long *sweeps);
+
+/* ---- CG (hot path 2) ---------------------------------------------------------------- */
+
+/* free_energy_pseudodensity + gsum (svirl/cuda/observables.h:251-362, observables.py:124-149) */
+int svl_free_energy(svl_ctx *ctx, double kappa2, double eps, const svl_buf *eps_field, double H,
+                    const svl_buf *psi, const svl_buf *abei, const svl_buf *ab, double *E_out);
+/* free_energy_jacobian_psi / _A (svirl/cuda/cg.h:16-121, 125-301); out is overwritten
+ * (the reference zero-fills then accumulates, cg.py:128,165). */
+int svl_jacobian_psi(svl_ctx *ctx, double kappa2, double eps, const svl_buf *eps_field, double H,
+                     const svl_buf *psi, const svl_buf *abei, const svl_buf *ab, svl_buf *out);
+int svl_jacobian_A(svl_ctx *ctx, double kappa2, double H, const svl_buf *psi, const svl_buf *abei,
+                   const svl_buf *ab, svl_buf *out);
+/* free_energy_conjgrad_coef_psi (cg.h:315-474): c[0..4]; _coef (cg.h:478-731): c[0..16] in the
+ * kernel's flat order c00..c04,c10..c14,c20..c24,c30,c40.  Quirk Q11: eps_field is ignored. */
+int svl_cg_coef_psi(svl_ctx *ctx, double kappa2, double eps, double H, const svl_buf *psi,
+                    const svl_buf *dpsi, const svl_buf *abei, const svl_buf *ab, double *c5_out);
+int svl_cg_coef(svl_ctx *ctx, double kappa2, double eps, double H, const svl_buf *psi, const svl_buf *dpsi,
+                const svl_buf *abei, const svl_buf *ab, const svl_buf *dab, double *c17_out);
+/* PR+ beta = max(sum g.(g-gp) / sum gp.gp, 0) (svirl/cuda/utils.h:13-70,140-146; cg.py:422-449);
+ * works on SVL_NODE_C and SVL_EDGE.  nan -> 0 like the device fmax. */
+int svl_cg_beta(svl_ctx *ctx, const svl_buf *g, const svl_buf *g_prev, double *beta_out);
+/* z = alpha*x - y (axmy_c/_r, utils.h:97-114) and z = alpha*x + y (axpy_c/_r, utils.h:74-92) */
+int svl_axmy(svl_ctx *ctx, const svl_buf *x, const svl_buf *y, svl_buf *z, double alpha);
+int svl_axpy(svl_ctx *ctx, const svl_buf *x, const svl_buf *y, svl_buf *z, double alpha);
+
+/* Fused CG iteration pieces (same arithmetic, fewer passes over HBM):
+ *  svl_cg_begin: jacobians at (psi, ab) -> g; beta vs g_prev (if have_prev); d <- beta*d - g;
+ *                17 (solveA) or 5 coefficients of the line-search polynomial -> c_out.
+ *  svl_cg_end:   psi += alpha_psi*d_psi, ab += alpha_A*d_A; energy of the new state -> E_out.
+ * The host keeps the reference's numpy/scipy line search between the two calls. */
+int svl_cg_begin(svl_ctx *ctx, int solveA, int have_prev, double kappa2, double eps, const svl_buf *eps_field,
+                 double H, const svl_buf *psi, const svl_buf *abei, const svl_buf *ab, svl_buf *g_psi,
+                 svl_buf *g_psi_prev, svl_buf *d_psi, svl_buf *g_A, svl_buf *g_A_prev, svl_buf *d_A,
+                 double *beta_inout /* [2]: psi, A */, double *c_out);
+int svl_cg_end(svl_ctx *ctx, int solveA, double kappa2, double eps, const svl_buf *eps_field, double H,
+               svl_buf *psi, const svl_buf *abei, svl_buf *ab, const svl_buf *d_psi, const svl_buf *d_A,
+               double alpha_psi, double alpha_A, double *E_out);
+
+/* ---- observables (svirl/cuda/observables.h:5-235) -------------------------------------- */
+int svl_magnetic_field(svl_ctx *ctx, const svl_buf *abei, const svl_buf *ab, svl_buf *B_out);
+int svl_current_density(svl_ctx *ctx, double kappa2, double H, const svl_buf *abei, const svl_buf *ab,
+                        svl_buf *j_out);
+int svl_supercurrent_density(svl_ctx *ctx, const svl_buf *psi, const svl_buf *abei, const svl_buf *ab,
+                             svl_buf *js_out);
+/* GPU pass of the vortex detector (svirl/observables/vortex_detector.py:55-72): writes the cell
+ * indices n = i + (Nx-1) j (ascending) of every cell whose winding number v satisfies the
+ * SUPERSET test |v| > 0.45 && |v - round(v)| < 0.15; the host re-tests candidates with the
+ * reference's exact arithmetic.  count_out may exceed max_out (then call again). */
+int svl_vortex_candidates(svl_ctx *ctx, double H, const svl_buf *psi, const svl_buf *ab, int64_t *cells_out,
+                          double *v_out, size_t max_out, size_t *count_out);
+
+/* ---- reductions (svirl/parallel/reduction.py:40-173): deterministic two-stage sums ------ */
+int svl_sum(svl_ctx *ctx, const svl_buf *in, size_t n, double *out);
+int svl_sum_v(svl_ctx *ctx, const svl_buf *in, size_t nv, int ne, double *out /* [ne] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVIRL_B200_H */

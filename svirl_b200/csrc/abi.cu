@@ -1,0 +1,320 @@
+// Context, buffers, copies, options: the non-arithmetic part of the C ABI.
+// Replaces svirl/parallel/startup.py (context), svirl/storage/arrays.py (device side),
+// svirl/parallel/utils.py (copy_dtod) of the reference.
+#include "common.cuh"
+#include <stdarg.h>
+
+static thread_local char g_err[1024] = "";
+
+void svl_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *svl_last_error(void) { return g_err; }
+extern "C" int svl_version(void) { return 100; }
+
+// ----------------------------------------------------------------------------- node flags
+__global__ void k_node_flags(Geo g, const uint8_t *mt, uint8_t *nf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int jl = blockIdx.y * blockDim.y + threadIdx.y;   // plane row
+    if (i >= g.P || jl >= g.rows) return;
+    int j = jl + g.rb;
+    uint8_t f = 0;
+    if (i < g.Nx && j >= 0 && j < g.Ny) {
+        bool mm = (i > 0) && (j > 0), mp = (i > 0) && (j + 1 < g.Ny);
+        bool pm = (i + 1 < g.Nx) && (j > 0), pp = (i + 1 < g.Nx) && (j + 1 < g.Ny);
+        if (mt) {   // cells are stored in a pitched plane too: cell (ci, cj) at g.at(ci, cj)
+            if (mm) mm = mt[g.at(i - 1, j - 1)] != 0;
+            if (mp) mp = mt[g.at(i - 1, j)] != 0;
+            if (pm) pm = mt[g.at(i, j - 1)] != 0;
+            if (pp) pp = mt[g.at(i, j)] != 0;
+        }
+        f = (mm ? NF_MM : 0) | (mp ? NF_MP : 0) | (pm ? NF_PM : 0) | (pp ? NF_PP : 0);
+    }
+    nf[(size_t)jl * g.P + i] = f;
+}
+
+extern "C" int svl_set_material(svl_ctx *c, const svl_buf *mt) {
+    SVL_REQUIRE(c, "null context");
+    SVL_REQUIRE(!mt || mt->kind == SVL_CELL_B, "material tiling must be a SVL_CELL_B buffer");
+    dim3 b(32, 8), gr((c->g.P + 31) / 32, (c->g.rows + 7) / 8);
+    k_node_flags<<<gr, b, 0, c->stream>>>(c->g, mt ? (const uint8_t *)mt->p[0] : nullptr, c->nf);
+    SVL_CHECK(cudaGetLastError());
+    c->have_mt = mt != nullptr;
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- lifecycle
+extern "C" int svl_create(svl_ctx **out, int device_id, int Nx, int Ny, double dx, double dy, int dtype_bytes,
+                          int j0, int j1) {
+    SVL_REQUIRE(out, "null out");
+    SVL_REQUIRE(dtype_bytes == 4 || dtype_bytes == 8, "dtype_bytes must be 4 or 8");
+    SVL_REQUIRE(Nx >= 4 && Ny >= 4, "Nx, Ny must be >= 4");
+    SVL_REQUIRE(0 <= j0 && j0 < j1 && j1 <= Ny, "bad slab rows");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        svl_set_error("no CUDA device available (%s): svirl_b200 has no CPU fallback", cudaGetErrorString(e));
+        return 3;
+    }
+    SVL_REQUIRE(device_id >= 0 && device_id < ndev, "bad device id");
+    SVL_CHECK(cudaSetDevice(device_id));
+    svl_ctx *c = new svl_ctx();
+    memset(c, 0, sizeof(*c));
+    c->device = device_id;
+    c->rsize = dtype_bytes;
+    Geo &g = c->g;
+    g.Nx = Nx; g.Ny = Ny; g.j0 = j0; g.j1 = j1;
+    g.rb = j0 - SVL_HALO;
+    g.rows = j1 - j0 + 2 * SVL_HALO;
+    g.P = ((Nx + 31) / 32) * 32;
+    g.dx = dx; g.dy = dy;
+    g.idx = 1.0 / dx; g.idy = 1.0 / dy;
+    g.idx2 = 1.0 / (dx * dx); g.idy2 = 1.0 / (dy * dy); g.idxy = 1.0 / (dx * dy);
+    SVL_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    size_t nfb = (size_t)g.rows * g.P;
+    SVL_CHECK(cudaMalloc(&c->nf, nfb));
+    SVL_CHECK(cudaMalloc(&c->d_result, 64 * sizeof(double)));
+    SVL_CHECK(cudaMallocHost(&c->h_result, 64 * sizeof(double)));
+    SVL_CHECK(cudaMalloc(&c->d_resid, SVL_MAX_SWEEPS * sizeof(unsigned long long)));
+    SVL_CHECK(cudaMallocHost(&c->h_resid, SVL_MAX_SWEEPS * sizeof(unsigned long long)));
+    SVL_CHECK(cudaMalloc(&c->d_counter, 16 * sizeof(unsigned int)));
+    SVL_CHECK(cudaMemsetAsync(c->d_counter, 0, 16 * sizeof(unsigned int), c->stream));
+    SVL_CHECK(cudaMalloc(&c->d_ncand, sizeof(unsigned long long)));
+    c->opt_psi_kernel = 0;
+    c->opt_psi_k = 4;
+    c->opt_tma = 1;
+    c->opt_graphs = 1;
+    c->pred_psi = 0;
+    c->pred_A = 0;
+    *out = c;
+    return svl_set_material(c, nullptr);
+}
+
+extern "C" int svl_destroy(svl_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int k = 0; k < 2; k++) {
+        if (c->psi_s[k]) svl_free(c, c->psi_s[k]);
+        if (c->ab_s[k]) svl_free(c, c->ab_s[k]);
+    }
+    cudaFree(c->nf); cudaFree(c->d_result); cudaFreeHost(c->h_result);
+    cudaFree(c->d_resid); cudaFreeHost(c->h_resid); cudaFree(c->d_counter);
+    cudaFree(c->partials); cudaFree(c->d_cand); cudaFree(c->d_candv); cudaFree(c->d_ncand);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+extern "C" int svl_synchronize(svl_ctx *c) {
+    SVL_REQUIRE(c, "null context");
+    SVL_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int svl_set_option(svl_ctx *c, const char *name, int v) {
+    SVL_REQUIRE(c && name, "null argument");
+    if (!strcmp(name, "psi_kernel")) c->opt_psi_kernel = v;
+    else if (!strcmp(name, "psi_k")) { SVL_REQUIRE(v >= 1 && v <= SVL_HALO, "psi_k out of range"); c->opt_psi_k = v; }
+    else if (!strcmp(name, "tma")) c->opt_tma = v;
+    else if (!strcmp(name, "graphs")) c->opt_graphs = v;
+    else if (!strcmp(name, "reset_prediction")) { c->pred_psi = 0; c->pred_A = 0; }
+    else { svl_set_error("unknown option %s", name); return 2; }
+    return 0;
+}
+
+extern "C" int svl_get_stat(svl_ctx *c, const char *name, double *v) {
+    SVL_REQUIRE(c && name && v, "null argument");
+    if (!strcmp(name, "launches")) *v = c->stat_launches;
+    else if (!strcmp(name, "replays")) *v = c->stat_replays;
+    else if (!strcmp(name, "psi_sweeps")) *v = c->stat_psi_sweeps;
+    else if (!strcmp(name, "A_sweeps")) *v = c->stat_A_sweeps;
+    else if (!strcmp(name, "pitch")) *v = c->g.P;
+    else if (!strcmp(name, "reset")) { c->stat_launches = c->stat_replays = c->stat_psi_sweeps = c->stat_A_sweeps = 0; *v = 0; }
+    else { svl_set_error("unknown stat %s", name); return 2; }
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- buffers
+static int kind_esize(const svl_ctx *c, int kind) {
+    switch (kind) {
+        case SVL_NODE_C: return 2 * c->rsize;
+        case SVL_NODE_R: case SVL_EDGE: case SVL_CELL_R: return c->rsize;
+        case SVL_CELL_B: return 1;
+    }
+    return 0;
+}
+
+// number of valid global rows / row width (elements) of plane `part` of a kind
+static void plane_shape(const svl_ctx *c, int kind, int part, int *nrows, int *width) {
+    const Geo &g = c->g;
+    switch (kind) {
+        case SVL_NODE_C: case SVL_NODE_R: *nrows = g.Ny; *width = g.Nx; break;
+        case SVL_EDGE:
+            if (part == 0) { *nrows = g.Ny; *width = g.Nx - 1; }
+            else { *nrows = g.Ny - 1; *width = g.Nx; }
+            break;
+        default: *nrows = g.Ny - 1; *width = g.Nx - 1; break;
+    }
+}
+
+extern "C" int svl_alloc(svl_ctx *c, int kind, size_t n, int elem_size, svl_buf **out) {
+    SVL_REQUIRE(c && out, "null argument");
+    SVL_REQUIRE(kind >= SVL_NODE_C && kind <= SVL_FLAT, "bad kind");
+    SVL_CHECK(cudaSetDevice(c->device));
+    svl_buf *b = new svl_buf();
+    memset(b, 0, sizeof(*b));
+    b->ctx = c; b->kind = kind;
+    const Geo &g = c->g;
+    if (kind == SVL_FLAT) {
+        SVL_REQUIRE(elem_size > 0, "elem_size required for SVL_FLAT");
+        b->esize = elem_size; b->n = n;
+        b->bytes[0] = (n ? n : 1) * (size_t)elem_size;
+    } else {
+        b->esize = kind_esize(c, kind);
+        size_t plane = (size_t)g.rows * g.P * b->esize;
+        b->bytes[0] = plane;
+        size_t N = (size_t)g.Nx * g.Ny;
+        switch (kind) {
+            case SVL_NODE_C: case SVL_NODE_R: b->n = N; break;
+            case SVL_EDGE: b->n = (size_t)(g.Nx - 1) * g.Ny + (size_t)g.Nx * (g.Ny - 1); b->bytes[1] = plane; break;
+            default: b->n = (size_t)(g.Nx - 1) * (g.Ny - 1); break;
+        }
+    }
+    for (int k = 0; k < 2; k++) {
+        if (!b->bytes[k]) continue;
+        cudaError_t e = cudaMalloc(&b->p[k], b->bytes[k]);
+        if (e != cudaSuccess) {
+            svl_set_error("cudaMalloc of %zu bytes failed: %s", b->bytes[k], cudaGetErrorString(e));
+            if (k == 1) cudaFree(b->p[0]);
+            delete b;
+            return 1;
+        }
+        SVL_CHECK(cudaMemsetAsync(b->p[k], 0, b->bytes[k], c->stream));
+    }
+    *out = b;
+    return 0;
+}
+
+extern "C" int svl_free(svl_ctx *c, svl_buf *b) {
+    if (!b) return 0;
+    if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    cudaFree(b->p[0]);
+    cudaFree(b->p[1]);
+    delete b;
+    return 0;
+}
+
+extern "C" size_t svl_buf_size(const svl_buf *b) { return b ? b->n : 0; }
+
+// Copy global rows [r0, r1) of one plane between the flat host layout and the pitched plane.
+static int copy_rows(svl_ctx *c, const svl_buf *b, int part, int r0, int r1, void *host, size_t host_row0,
+                     bool to_device) {
+    int nrows, width;
+    plane_shape(c, b->kind, part, &nrows, &width);
+    const Geo &g = c->g;
+    int lo = r0 > g.rb ? r0 : g.rb, hi = r1 < g.rb + g.rows ? r1 : g.rb + g.rows;
+    if (lo < 0) lo = 0;
+    if (hi > nrows) hi = nrows;
+    if (hi <= lo) return 0;
+    size_t wbytes = (size_t)width * b->esize, pbytes = (size_t)g.P * b->esize;
+    char *d = (char *)b->p[part] + (size_t)(lo - g.rb) * pbytes;
+    char *h = (char *)host + ((size_t)lo - host_row0) * wbytes;
+    if (to_device) SVL_CHECK(cudaMemcpy2DAsync(d, pbytes, h, wbytes, wbytes, hi - lo, cudaMemcpyHostToDevice, c->stream));
+    else SVL_CHECK(cudaMemcpy2DAsync(h, wbytes, d, pbytes, wbytes, hi - lo, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
+extern "C" int svl_h2d(svl_ctx *c, svl_buf *dst, const void *src) {
+    SVL_REQUIRE(c && dst && src, "null argument");
+    SVL_CHECK(cudaSetDevice(c->device));
+    if (dst->kind == SVL_FLAT) {
+        SVL_CHECK(cudaMemcpyAsync(dst->p[0], src, dst->n * dst->esize, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        const Geo &g = c->g;
+        // device gets owned rows plus whatever halo rows exist globally
+        SVL_TRY(copy_rows(c, dst, 0, g.rb, g.rb + g.rows, (void *)src, 0, true));
+        if (dst->kind == SVL_EDGE) {
+            const char *sb = (const char *)src + (size_t)(g.Nx - 1) * g.Ny * dst->esize;
+            SVL_TRY(copy_rows(c, dst, 1, g.rb, g.rb + g.rows, (void *)sb, 0, true));
+        }
+    }
+    SVL_CHECK(cudaStreamSynchronize(c->stream));   // host buffer may be pageable / reused by the caller
+    return 0;
+}
+
+extern "C" int svl_d2h(svl_ctx *c, void *dst, const svl_buf *src) {
+    SVL_REQUIRE(c && dst && src, "null argument");
+    SVL_CHECK(cudaSetDevice(c->device));
+    if (src->kind == SVL_FLAT) {
+        SVL_CHECK(cudaMemcpyAsync(dst, src->p[0], src->n * src->esize, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        const Geo &g = c->g;
+        SVL_TRY(copy_rows(c, src, 0, g.j0, g.j1, dst, 0, false));   // owned rows only
+        if (src->kind == SVL_EDGE) {
+            char *db = (char *)dst + (size_t)(g.Nx - 1) * g.Ny * src->esize;
+            SVL_TRY(copy_rows(c, src, 1, g.j0, g.j1, db, 0, false));
+        }
+    }
+    SVL_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int svl_h2d_rows(svl_ctx *c, svl_buf *dst, int part, int r0, int r1, const void *src) {
+    SVL_REQUIRE(c && dst && src && dst->kind != SVL_FLAT, "bad argument");
+    SVL_REQUIRE(part == 0 || (part == 1 && dst->kind == SVL_EDGE), "bad part");
+    SVL_CHECK(cudaSetDevice(c->device));
+    SVL_TRY(copy_rows(c, dst, part, r0, r1, (void *)src, (size_t)r0, true));
+    SVL_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int svl_d2h_rows(svl_ctx *c, void *dst, const svl_buf *src, int part, int r0, int r1) {
+    SVL_REQUIRE(c && dst && src && src->kind != SVL_FLAT, "bad argument");
+    SVL_REQUIRE(part == 0 || (part == 1 && src->kind == SVL_EDGE), "bad part");
+    SVL_CHECK(cudaSetDevice(c->device));
+    SVL_TRY(copy_rows(c, src, part, r0, r1, dst, (size_t)r0, false));
+    SVL_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int svl_d2d(svl_ctx *c, svl_buf *dst, const svl_buf *src) {
+    SVL_REQUIRE(c && dst && src, "null argument");
+    SVL_REQUIRE(dst->kind == src->kind && dst->bytes[0] == src->bytes[0] && dst->bytes[1] == src->bytes[1],
+                "d2d: buffers differ in kind/size");
+    for (int k = 0; k < 2; k++)
+        if (src->bytes[k])
+            SVL_CHECK(cudaMemcpyAsync(dst->p[k], src->p[k], src->bytes[k], cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
+extern "C" int svl_fill_zero(svl_ctx *c, svl_buf *b) {
+    SVL_REQUIRE(c && b, "null argument");
+    for (int k = 0; k < 2; k++)
+        if (b->bytes[k]) SVL_CHECK(cudaMemsetAsync(b->p[k], 0, b->bytes[k], c->stream));
+    return 0;
+}
+
+extern "C" int svl_swap(svl_ctx *c, svl_buf *x, svl_buf *y) {
+    SVL_REQUIRE(c && x && y, "null argument");
+    SVL_REQUIRE(x->kind == y->kind && x->bytes[0] == y->bytes[0] && x->bytes[1] == y->bytes[1],
+                "swap: buffers differ in kind/size");
+    for (int k = 0; k < 2; k++) { void *t = x->p[k]; x->p[k] = y->p[k]; y->p[k] = t; }
+    return 0;
+}
+
+int svl_scratch_node(svl_ctx *c, int k, svl_buf **out) {
+    if (!c->psi_s[k]) SVL_TRY(svl_alloc(c, SVL_NODE_C, 0, 0, &c->psi_s[k]));
+    *out = c->psi_s[k];
+    return 0;
+}
+
+int svl_scratch_edge(svl_ctx *c, int k, svl_buf **out) {
+    if (!c->ab_s[k]) SVL_TRY(svl_alloc(c, SVL_EDGE, 0, 0, &c->ab_s[k]));
+    *out = c->ab_s[k];
+    return 0;
+}

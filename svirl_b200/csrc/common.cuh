@@ -1,0 +1,187 @@
+// Shared declarations of the svirl_b200 CUDA library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include "../../include/svirl_b200.h"
+
+#define SVL_HALO 8            // halo rows kept above/below the owned rows of every plane (>= max fused sweeps)
+#define SVL_MAX_SWEEPS 1024   // svirl/solvers/td.py:164, 274
+
+// ----------------------------------------------------------------------------- errors
+void svl_set_error(const char *fmt, ...);
+#define SVL_CHECK(call)                                                                        \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            svl_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return 1;                                                                          \
+        }                                                                                      \
+    } while (0)
+#define SVL_REQUIRE(cond, msg)                                              \
+    do {                                                                    \
+        if (!(cond)) {                                                      \
+            svl_set_error("%s:%d: %s", __FILE__, __LINE__, msg);            \
+            return 2;                                                       \
+        }                                                                   \
+    } while (0)
+#define SVL_TRY(call)            \
+    do {                         \
+        int rc_ = (call);        \
+        if (rc_) return rc_;     \
+    } while (0)
+
+// ----------------------------------------------------------------------------- geometry
+// Passed by value to every kernel.  Planes are pitched: element (i, j) of any plane lives at
+// (j - rb) * P + i, where rb = j0 - SVL_HALO is the global row stored in plane row 0.
+struct Geo {
+    int Nx, Ny;        // global node counts
+    int j0, j1;        // owned node rows [j0, j1)
+    int rb;            // global row of plane row 0
+    int P;             // pitch in elements (multiple of 32)
+    int rows;          // plane rows = j1 - j0 + 2*SVL_HALO
+    double dx, dy, idx, idy, idx2, idy2, idxy;
+    __host__ __device__ __forceinline__ size_t at(int i, int j) const { return (size_t)(j - rb) * P + i; }
+};
+
+template <typename R> struct V2;
+template <> struct V2<float>  { typedef float2 type; };
+template <> struct V2<double> { typedef double2 type; };
+
+// node flag bits (svirl/cuda/td.h:48-57)
+#define NF_MM 1
+#define NF_MP 2
+#define NF_PM 4
+#define NF_PP 8
+
+struct svl_buf {
+    svl_ctx *ctx;
+    int kind;
+    int esize;          // bytes per element
+    size_t n;           // elements in the flat (reference) layout
+    void *p[2];         // plane(s): [0] nodes/cells/a/flat, [1] b
+    size_t bytes[2];
+};
+
+struct svl_ctx {
+    int device;
+    int rsize;                     // 4 or 8
+    Geo g;
+    cudaStream_t stream;
+    // per-node material flags (always present)
+    uint8_t *nf;
+    bool have_mt;
+    // scratch for solvers (allocated lazily)
+    svl_buf *psi_s[2];
+    svl_buf *ab_s[2];
+    // reductions
+    double *partials;              // device, capacity partial_cap doubles
+    size_t partial_cap;
+    double *d_result;              // device, 64 doubles
+    double *h_result;              // pinned, 64 doubles
+    unsigned long long *d_resid;   // device, SVL_MAX_SWEEPS slots (bit patterns of non-negative doubles)
+    unsigned long long *h_resid;   // pinned
+    unsigned int *d_counter;       // last-block-done counters
+    // vortex candidates
+    long long *d_cand; double *d_candv; unsigned long long *d_ncand; size_t cand_cap;
+    // options / stats
+    int opt_psi_kernel, opt_psi_k, opt_tma, opt_graphs;
+    int pred_psi, pred_A;          // predicted sweep counts (from the previous time step)
+    double stat_launches, stat_replays, stat_psi_sweeps, stat_A_sweeps;
+};
+
+static inline int svl_nblocks(size_t n, int b) { return (int)((n + b - 1) / b); }
+
+// td.cu
+int svl_launch_psi_sweep(svl_ctx *c, double dt, double eps, const svl_buf *epsf, const svl_buf *ab,
+                         const svl_buf *rhs, const svl_buf *psi, svl_buf *out, double lang_c,
+                         uint32_t rand_t, unsigned long long *resid_slot);
+int svl_launch_a_sweep(svl_ctx *c, double dt, double kappa2, double rho, double H, const svl_buf *psi,
+                       const svl_buf *ph, const svl_buf *rhs, const svl_buf *ab, svl_buf *out,
+                       double lang_c, uint32_t rand_t, int write_rhs, unsigned long long *resid_slot);
+// reduce.cu
+int svl_ensure_partials(svl_ctx *c, size_t n);
+int svl_finish_sum(svl_ctx *c, int nblocks, int nv, double scale, double *out_host);  // partials[nblocks*nv] -> host
+// abi.cu
+int svl_scratch_node(svl_ctx *c, int k, svl_buf **out);
+int svl_scratch_edge(svl_ctx *c, int k, svl_buf **out);
+
+// ----------------------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+template <typename R> __device__ __forceinline__ void sincos_r(R x, R *s, R *c);
+template <> __device__ __forceinline__ void sincos_r<float>(float x, float *s, float *c) { sincosf(x, s, c); }
+template <> __device__ __forceinline__ void sincos_r<double>(double x, double *s, double *c) { sincos(x, s, c); }
+
+// Thomas Wang hash RNG of the reference (svirl/cuda/common.h:36-63): exact integer maths.
+__device__ __forceinline__ uint32_t wang_hash(uint32_t s) {
+    s = (s ^ 61u) ^ (s >> 16);
+    s *= 9u;
+    s = s ^ (s >> 4);
+    s *= 0x27d4eb2du;
+    s = s ^ (s >> 15);
+    return s;
+}
+template <typename R> __device__ __forceinline__ R rand_1(uint32_t n, uint32_t t) {
+    return (R)(0.00000000023283064365386962890625 * (double)(R)wang_hash(71u * n + 9887u * t));
+}
+template <typename R> __device__ __forceinline__ R rand_2(uint32_t n, uint32_t t) {
+    return (R)(0.00000000023283064365386962890625 * (double)(R)wang_hash(73u * n + 9901u * t + 1u));
+}
+
+// Im(conj(p0) U(ph) p1)  (svirl/cuda/common.h:65-73)
+template <typename R, typename C>
+__device__ __forceinline__ R js_link(C p0, R ph, C p1) {
+    R s, c;
+    sincos_r<R>(ph, &s, &c);
+    return (p0.x * p1.y - p0.y * p1.x) * c - (p0.x * p1.x + p0.y * p1.y) * s;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block max of non-negative values -> one atomicMax per CTA on the bit pattern (exact, order-free).
+__device__ __forceinline__ void block_max_to_slot(double r, unsigned long long *slot) {
+    __shared__ double sm_max[32];
+    int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+    r = warp_max(r);
+    if ((tid & 31) == 0) sm_max[tid >> 5] = r;
+    __syncthreads();
+    if (tid < 32) {
+        r = (tid < (nt + 31) / 32) ? sm_max[tid] : 0.0;
+        r = warp_max(r);
+        if (tid == 0 && r > 0.0) atomicMax(slot, (unsigned long long)__double_as_longlong(r));
+    }
+}
+
+// Block sum of NV doubles per thread -> partials[block * NV + k] (fixed order => deterministic).
+template <int NV>
+__device__ __forceinline__ void block_sum_to_partials(double (&v)[NV], double *partials, int block_id) {
+    __shared__ double sm_sum[32 * NV];
+    int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+    int lane = tid & 31, w = tid >> 5, nw = (nt + 31) / 32;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        double x = warp_sum(v[k]);
+        if (lane == 0) sm_sum[w * NV + k] = x;
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            double x = (lane < nw) ? sm_sum[lane * NV + k] : 0.0;
+            x = warp_sum(x);
+            if (lane == 0) partials[(size_t)block_id * NV + k] = x;
+        }
+    }
+}
+#endif

@@ -1,0 +1,402 @@
+// TDGL time step: Jacobi sweeps of the psi and A equations and the solve drivers.
+// Reference: svirl/cuda/td.h:5-133 (psi sweep), :311-463 (A sweep),
+//            svirl/solvers/td.py:157-218, 252-325, 342-367 (drivers).
+#include "common.cuh"
+
+int svl_launch_psi_stream(svl_ctx *c, int K, double dt, double eps, const svl_buf *epsf, const svl_buf *ab,
+                          const svl_buf *rhs, const svl_buf *psi, svl_buf *out, double lang_c, uint32_t rand_t,
+                          unsigned long long *resid_slots);   // psi_stream.cu
+
+// ----------------------------------------------------------------------------- plain psi sweep
+// One thread per node; neighbours come through L1/L2.  NOISE: 0 none, 1 add + write back to rhs
+// (kernel-level API at jstep 0), 2 add on every sweep without write back (solver: rhs may alias psi).
+template <typename R, int NOISE>
+__global__ void __launch_bounds__(256)
+k_psi_sweep(Geo g, R dt, R eps, const R *__restrict__ epsf, const uint8_t *__restrict__ nf,
+            const R *__restrict__ pa, const R *__restrict__ pb, typename V2<R>::type *rhs,
+            const typename V2<R>::type *psi, typename V2<R>::type *out, R lang_c, uint32_t rand_t,
+            unsigned long long *slot) {
+    typedef typename V2<R>::type C;
+    const R dx = (R)g.dx, dy = (R)g.dy, idx2 = (R)g.idx2, idy2 = (R)g.idy2;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = g.j0 + blockIdx.y * blockDim.y + threadIdx.y;
+    double r = 0.0;
+    if (i < g.Nx && j < g.j1) {
+        size_t n = g.at(i, j);
+        unsigned f = nf[n];
+        C p00 = psi[n];
+        C nx;
+        nx.x = 0; nx.y = 0;
+        if (f) {
+            C q = rhs[n];
+            if (NOISE) {
+                if (lang_c > (R)1.0e-32) {
+                    uint32_t nn = (uint32_t)i + (uint32_t)g.Nx * (uint32_t)j;
+                    q.x += lang_c * (rand_1<R>(nn, rand_t) - (R)0.5);
+                    q.y += lang_c * (rand_2<R>(nn, rand_t) - (R)0.5);
+                    if (NOISE == 1) rhs[n] = q;
+                }
+            }
+            bool wW = f & (NF_MM | NF_MP), wE = f & (NF_PM | NF_PP);
+            bool wS = f & (NF_MM | NF_PM), wN = f & (NF_MP | NF_PP);
+            R e = epsf ? epsf[n] : eps;
+            R sx = 0, sy = 0, tx = 0, ty = 0, s, c;
+            if (wW) {   // U(-dx a[i-1,j]) psi[i-1,j] = (c + i s) psi
+                C p = psi[n - 1];
+                sincos_r<R>(dx * pa[n - 1], &s, &c);
+                sx += c * p.x - s * p.y; sy += c * p.y + s * p.x;
+            }
+            if (wE) {   // U(dx a[i,j]) psi[i+1,j] = (c - i s) psi
+                C p = psi[n + 1];
+                sincos_r<R>(dx * pa[n], &s, &c);
+                sx += c * p.x + s * p.y; sy += c * p.y - s * p.x;
+            }
+            if (wS) {
+                C p = psi[n - g.P];
+                sincos_r<R>(dy * pb[n - g.P], &s, &c);
+                tx += c * p.x - s * p.y; ty += c * p.y + s * p.x;
+            }
+            if (wN) {
+                C p = psi[n + g.P];
+                sincos_r<R>(dy * pb[n], &s, &c);
+                tx += c * p.x + s * p.y; ty += c * p.y - s * p.x;
+            }
+            R diag = (R)1.0 + dt * (q.x * q.x + q.y * q.y - e
+                                    + (idx2 * (R)((int)wW + (int)wE) + idy2 * (R)((int)wS + (int)wN)));
+            nx.x = (q.x + dt * (idx2 * sx + idy2 * tx)) / diag;
+            nx.y = (q.y + dt * (idx2 * sy + idy2 * ty)) / diag;
+        }
+        out[n] = nx;
+        r = fmax(fabs((double)(nx.x - p00.x)), fabs((double)(nx.y - p00.y)));
+    }
+    block_max_to_slot(r, slot);
+}
+
+template <typename R>
+static int launch_psi_plain(svl_ctx *c, double dt, double eps, const svl_buf *epsf, const svl_buf *ab,
+                            const svl_buf *rhs, const svl_buf *psi, svl_buf *out, double lang_c,
+                            uint32_t rand_t, int noise, unsigned long long *slot) {
+    typedef typename V2<R>::type C;
+    const Geo &g = c->g;
+    dim3 b(32, 8), gr((g.Nx + 31) / 32, (g.j1 - g.j0 + 7) / 8);
+#define ARGS g, (R)dt, (R)eps, epsf ? (const R *)epsf->p[0] : nullptr, c->nf, (const R *)ab->p[0], \
+             (const R *)ab->p[1], (C *)rhs->p[0], (const C *)psi->p[0], (C *)out->p[0], (R)lang_c, rand_t, slot
+    if (noise == 0) k_psi_sweep<R, 0><<<gr, b, 0, c->stream>>>(ARGS);
+    else if (noise == 1) k_psi_sweep<R, 1><<<gr, b, 0, c->stream>>>(ARGS);
+    else k_psi_sweep<R, 2><<<gr, b, 0, c->stream>>>(ARGS);
+#undef ARGS
+    SVL_CHECK(cudaGetLastError());
+    c->stat_launches += 1;
+    return 0;
+}
+
+int svl_launch_psi_sweep(svl_ctx *c, double dt, double eps, const svl_buf *epsf, const svl_buf *ab,
+                         const svl_buf *rhs, const svl_buf *psi, svl_buf *out, double lang_c, uint32_t rand_t,
+                         unsigned long long *slot) {
+    int noise = lang_c > 1.0e-32 ? 2 : 0;
+    if (c->rsize == 4) return launch_psi_plain<float>(c, dt, eps, epsf, ab, rhs, psi, out, lang_c, rand_t, noise, slot);
+    return launch_psi_plain<double>(c, dt, eps, epsf, ab, rhs, psi, out, lang_c, rand_t, noise, slot);
+}
+
+// ----------------------------------------------------------------------------- A sweep
+// One thread per node (i,j) updates the a-edge and the b-edge whose tail is that node.
+// ph_a/ph_b (the reference's abi_ab_rhs) may alias oa/ob: each thread reads its own entry
+// before it writes it and nobody else reads that entry (quirk Q1).
+template <typename R, int NOISE>
+__global__ void __launch_bounds__(256)
+k_a_sweep(Geo g, R dt, R kappa2, R rho, R H, const uint8_t *__restrict__ nf,
+          const typename V2<R>::type *__restrict__ psi, const R *ph_a, const R *ph_b, R *rhs_a, R *rhs_b,
+          const R *a, const R *b, R *oa, R *ob, R lang_c, uint32_t rand_t, unsigned long long *slot) {
+    typedef typename V2<R>::type C;
+    const R dx = (R)g.dx, dy = (R)g.dy, idx = (R)g.idx, idy = (R)g.idy, idx2 = (R)g.idx2, idy2 = (R)g.idy2,
+            idxy = (R)g.idxy;
+    const R dt_rho = dt * rho, dtrk = dt_rho * kappa2;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = g.j0 + blockIdx.y * blockDim.y + threadIdx.y;
+    double r = 0.0;
+    if (i < g.Nx && j < g.j1) {
+        size_t n = g.at(i, j);
+        const int P = g.P;
+        unsigned f = nf[n];
+        C p0 = psi[n];
+        if (i < g.Nx - 1) {
+            R q = rhs_a[n];
+            if (NOISE) {
+                if (lang_c > (R)1.0e-32) {
+                    uint32_t ne = (uint32_t)i + (uint32_t)(g.Nx - 1) * (uint32_t)j;
+                    q += lang_c * (rand_1<R>(ne, rand_t) - (R)0.5);
+                    if (NOISE == 1) rhs_a[n] = q;
+                }
+            }
+            R rh = 0, dd = 1;
+            if (j == 0) { rh = (R)2.0 * kappa2 * H * idy; dd = 2; }
+            else if (j + 1 == g.Ny) { rh = -(R)2.0 * kappa2 * H * idy; dd = 2; }
+            R jl = 0;
+            if (f & (NF_PM | NF_PP)) jl = idx * js_link<R, C>(p0, dx * ph_a[n], psi[n + 1]);
+            R lo = 0, hi = 0;
+            if (j > 0) lo = idy2 * a[n - P] - idxy * b[n - P] + idxy * b[n - P + 1];
+            if (j + 1 < g.Ny) hi = idy2 * a[n + P] + idxy * b[n] - idxy * b[n + 1];
+            R nx = (q + dt_rho * (jl + rh) + dtrk * dd * (lo + hi)) / ((R)1.0 + (R)2.0 * dtrk * idy2);
+            R old = a[n];
+            oa[n] = nx;
+            r = fabs((double)(nx - old));
+        }
+        if (j < g.Ny - 1) {
+            R q = rhs_b[n];
+            if (NOISE) {
+                if (lang_c > (R)1.0e-32) {
+                    uint32_t ne = (uint32_t)((size_t)(g.Nx - 1) * g.Ny) + (uint32_t)i + (uint32_t)g.Nx * (uint32_t)j;
+                    q += lang_c * (rand_2<R>(ne, rand_t) - (R)0.5);
+                    if (NOISE == 1) rhs_b[n] = q;
+                }
+            }
+            R rh = 0, dd = 1;
+            if (i == 0) { rh = -(R)2.0 * kappa2 * H * idx; dd = 2; }
+            else if (i + 1 == g.Nx) { rh = (R)2.0 * kappa2 * H * idx; dd = 2; }
+            R jl = 0;
+            if (f & (NF_MP | NF_PP)) jl = idy * js_link<R, C>(p0, dy * ph_b[n], psi[n + P]);
+            R lo = 0, hi = 0;
+            if (i > 0) lo = idx2 * b[n - 1] - idxy * a[n - 1] + idxy * a[n - 1 + P];
+            if (i + 1 < g.Nx) hi = idx2 * b[n + 1] + idxy * a[n] - idxy * a[n + P];
+            R nx = (q + dt_rho * (jl + rh) + dtrk * dd * (lo + hi)) / ((R)1.0 + (R)2.0 * dtrk * idx2);
+            R old = b[n];
+            ob[n] = nx;
+            r = fmax(r, fabs((double)(nx - old)));
+        }
+    }
+    block_max_to_slot(r, slot);
+}
+
+template <typename R>
+static int launch_a(svl_ctx *c, double dt, double kappa2, double rho, double H, const svl_buf *psi,
+                    const svl_buf *ph, const svl_buf *rhs, const svl_buf *ab, svl_buf *out, double lang_c,
+                    uint32_t rand_t, int noise, unsigned long long *slot) {
+    typedef typename V2<R>::type C;
+    const Geo &g = c->g;
+    dim3 b(32, 8), gr((g.Nx + 31) / 32, (g.j1 - g.j0 + 7) / 8);
+#define ARGS g, (R)dt, (R)kappa2, (R)rho, (R)H, c->nf, (const C *)psi->p[0], (const R *)ph->p[0], (const R *)ph->p[1], \
+             (R *)rhs->p[0], (R *)rhs->p[1], (const R *)ab->p[0], (const R *)ab->p[1], (R *)out->p[0], (R *)out->p[1],  \
+             (R)lang_c, rand_t, slot
+    if (noise == 0) k_a_sweep<R, 0><<<gr, b, 0, c->stream>>>(ARGS);
+    else if (noise == 1) k_a_sweep<R, 1><<<gr, b, 0, c->stream>>>(ARGS);
+    else k_a_sweep<R, 2><<<gr, b, 0, c->stream>>>(ARGS);
+#undef ARGS
+    SVL_CHECK(cudaGetLastError());
+    c->stat_launches += 1;
+    return 0;
+}
+
+int svl_launch_a_sweep(svl_ctx *c, double dt, double kappa2, double rho, double H, const svl_buf *psi,
+                       const svl_buf *ph, const svl_buf *rhs, const svl_buf *ab, svl_buf *out, double lang_c,
+                       uint32_t rand_t, int noise, unsigned long long *slot) {
+    if (c->rsize == 4) return launch_a<float>(c, dt, kappa2, rho, H, psi, ph, rhs, ab, out, lang_c, rand_t, noise, slot);
+    return launch_a<double>(c, dt, kappa2, rho, H, psi, ph, rhs, ab, out, lang_c, rand_t, noise, slot);
+}
+
+// ----------------------------------------------------------------------------- stop rule
+// Exact reference decision (td.h:124-132 + td.py:198-201): int32(real_t(1e4*r/eps) clamped at 1e8)
+// and 1e-4*int < 1  <=>  int < 10000.
+static bool stop_rule(const svl_ctx *c, double r, double eps) {
+    double v;
+    if (c->rsize == 4) v = (double)(float)(1.0e4 * r / (double)(float)eps);
+    else v = 1.0e4 * r / eps;
+    if (v > 1.0e8) v = 1.0e8;
+    return (int)v < 10000;
+}
+
+static inline double slot_value(unsigned long long bits) {
+    double d;
+    memcpy(&d, &bits, sizeof(d));
+    return d;
+}
+
+static int read_resid(svl_ctx *c, int first, int count) {
+    SVL_CHECK(cudaMemcpyAsync(c->h_resid + first, c->d_resid + first, (size_t)count * sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, c->stream));
+    SVL_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int check_kinds(const svl_buf *psi, const svl_buf *ab, const svl_buf *epsf) {
+    SVL_REQUIRE(psi && psi->kind == SVL_NODE_C, "psi must be SVL_NODE_C");
+    SVL_REQUIRE(ab && ab->kind == SVL_EDGE, "ab must be SVL_EDGE");
+    SVL_REQUIRE(!epsf || epsf->kind == SVL_NODE_R, "eps_field must be SVL_NODE_R");
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- single-sweep ABI
+extern "C" int svl_td_psi_sweep(svl_ctx *c, double dt, double eps, const svl_buf *epsf, const svl_buf *ab,
+                                svl_buf *rhs, const svl_buf *psi, svl_buf *out, double lang_c, uint32_t jstep,
+                                uint32_t rand_t, double *r_out) {
+    SVL_REQUIRE(c, "null context");
+    SVL_TRY(check_kinds(psi, ab, epsf));
+    SVL_REQUIRE(rhs && rhs->kind == SVL_NODE_C && out && out->kind == SVL_NODE_C, "rhs/out must be SVL_NODE_C");
+    SVL_REQUIRE(out != psi, "psi_next must differ from psi");
+    SVL_CHECK(cudaMemsetAsync(c->d_resid, 0, sizeof(unsigned long long), c->stream));
+    int noise = (jstep == 0 && lang_c > 1.0e-32) ? 1 : 0;
+    if (c->rsize == 4) SVL_TRY(launch_psi_plain<float>(c, dt, eps, epsf, ab, rhs, psi, out, lang_c, rand_t, noise, c->d_resid));
+    else SVL_TRY(launch_psi_plain<double>(c, dt, eps, epsf, ab, rhs, psi, out, lang_c, rand_t, noise, c->d_resid));
+    SVL_TRY(read_resid(c, 0, 1));
+    if (r_out) *r_out = slot_value(c->h_resid[0]);
+    return 0;
+}
+
+extern "C" int svl_td_a_sweep(svl_ctx *c, double dt, double kappa2, double rho, double H, const svl_buf *psi,
+                              const svl_buf *ph, svl_buf *rhs, const svl_buf *ab, svl_buf *out, double lang_c,
+                              uint32_t jstep, uint32_t rand_t, double *r_out) {
+    SVL_REQUIRE(c, "null context");
+    SVL_REQUIRE(psi && psi->kind == SVL_NODE_C, "psi must be SVL_NODE_C");
+    SVL_REQUIRE(ph && rhs && ab && out && ph->kind == SVL_EDGE && rhs->kind == SVL_EDGE && ab->kind == SVL_EDGE &&
+                out->kind == SVL_EDGE, "edge buffers required");
+    SVL_REQUIRE(out != ab, "ab_next must differ from ab");
+    SVL_CHECK(cudaMemsetAsync(c->d_resid, 0, sizeof(unsigned long long), c->stream));
+    int noise = (jstep == 0 && lang_c > 1.0e-32) ? 1 : 0;
+    SVL_TRY(svl_launch_a_sweep(c, dt, kappa2, rho, H, psi, ph, rhs, ab, out, lang_c, rand_t, noise, c->d_resid));
+    SVL_TRY(read_resid(c, 0, 1));
+    if (r_out) *r_out = slot_value(c->h_resid[0]);
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- psi solve
+// Storage rotation instead of the reference's copy + ping-pong: B0 holds iterate 0 and is also
+// the right-hand side; sweep s reads in(s) and writes out(s):
+//   in(0) = B0, in(s odd) = S1, in(s even >= 2) = S2;   out(s even) = S1, out(s odd) = S2.
+// The host reads the per-sweep residual maxima once per solve: sweeps are launched up to the
+// count predicted from the previous time step, and the exact reference stop sweep is
+// recovered afterwards (the input of the last sweep is still intact, so an overshoot by one
+// is free; a larger overshoot replays from B0; an undershoot continues sweep by sweep).
+struct PsiSolveArgs {
+    double dt, eps; const svl_buf *epsf; const svl_buf *ab; double lang_c; uint32_t rand_t;
+};
+
+static int psi_launch_range(svl_ctx *c, const PsiSolveArgs &A, svl_buf *B0, svl_buf *S1, svl_buf *S2, int s0, int s1) {
+    // sweeps [s0, s1); uses the temporally blocked kernel for runs of K sweeps when enabled
+    int s = s0;
+    while (s < s1) {
+        const svl_buf *in = s == 0 ? B0 : ((s & 1) ? S1 : S2);
+        int K = 1;
+        if (c->opt_psi_kernel == 1) { K = c->opt_psi_k; if (K > s1 - s) K = s1 - s; }
+        svl_buf *out = ((s + K - 1) & 1) ? S2 : S1;      // out(s + K - 1)
+        if (c->opt_psi_kernel == 1) {
+            SVL_TRY(svl_launch_psi_stream(c, K, A.dt, A.eps, A.epsf, A.ab, B0, in, out, A.lang_c, A.rand_t, c->d_resid + s));
+        } else {
+            SVL_TRY(svl_launch_psi_sweep(c, A.dt, A.eps, A.epsf, A.ab, B0, in, out, A.lang_c, A.rand_t, c->d_resid + s));
+        }
+        s += K;
+    }
+    return 0;
+}
+
+extern "C" int svl_td_psi_solve(svl_ctx *c, double dt, double eps, const svl_buf *epsf, const svl_buf *ab,
+                                svl_buf *psi, double lang_c, uint32_t rand_t, double stop_eps, int *sweeps_out) {
+    SVL_REQUIRE(c, "null context");
+    SVL_TRY(check_kinds(psi, ab, epsf));
+    svl_buf *S1, *S2;
+    SVL_TRY(svl_scratch_node(c, 0, &S1));
+    SVL_TRY(svl_scratch_node(c, 1, &S2));
+    PsiSolveArgs A = {dt, eps, epsf, ab, lang_c, rand_t};
+    SVL_CHECK(cudaMemsetAsync(c->d_resid, 0, SVL_MAX_SWEEPS * sizeof(unsigned long long), c->stream));
+    int done = 0, nstop = -1;
+    int pred = c->pred_psi;
+    if (pred > SVL_MAX_SWEEPS) pred = SVL_MAX_SWEEPS;
+    while (nstop < 0) {
+        int upto = done == 0 && pred > 0 ? pred : done + 1;
+        if (upto > SVL_MAX_SWEEPS) upto = SVL_MAX_SWEEPS;
+        SVL_TRY(psi_launch_range(c, A, psi, S1, S2, done, upto));
+        SVL_TRY(read_resid(c, done, upto - done));
+        for (int s = done; s < upto; s++)
+            if (stop_rule(c, slot_value(c->h_resid[s]), stop_eps)) { nstop = s + 1; break; }
+        done = upto;
+        if (nstop < 0 && done >= SVL_MAX_SWEEPS) nstop = SVL_MAX_SWEEPS;   // reference: loop exhausts, keeps last iterate
+    }
+    // iterate nstop lives in out(nstop-1); `done` sweeps were executed
+    if (nstop < done) {
+        int lastK = 1;   // granularity of the final launch: result recoverable only at launch boundaries
+        if (nstop == done - 1 && !(c->opt_psi_kernel == 1 && c->opt_psi_k > 1)) {
+            // overshoot by one single sweep: the input of the last sweep is iterate nstop, still intact
+            (void)lastK;
+        } else {
+            c->stat_replays += 1;
+            SVL_TRY(psi_launch_range(c, A, psi, S1, S2, 0, nstop));
+        }
+    }
+    svl_buf *res = ((nstop - 1) & 1) ? S2 : S1;
+    SVL_TRY(svl_swap(c, psi, res));
+    c->pred_psi = nstop;
+    c->stat_psi_sweeps += nstop;
+    if (sweeps_out) *sweeps_out = nstop;
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- A solve
+//   in(0) = B0 (= right-hand side), in(s odd) = S1, in(s even >= 2) = S2; out(s even) = S1, out(s odd) = S2
+//   phase(s) = iterate s - (s mod 2)  (quirk Q1)  = B0 for s <= 1, else S2 (which IS out(s) for odd s).
+struct ASolveArgs {
+    double dt, kappa2, rho, H; const svl_buf *psi; double lang_c; uint32_t rand_t;
+};
+
+static int a_launch_range(svl_ctx *c, const ASolveArgs &A, svl_buf *B0, svl_buf *S1, svl_buf *S2, int s0, int s1) {
+    int noise = A.lang_c > 1.0e-32 ? 2 : 0;
+    for (int s = s0; s < s1; s++) {
+        const svl_buf *in = s == 0 ? B0 : ((s & 1) ? S1 : S2);
+        svl_buf *out = (s & 1) ? S2 : S1;
+        const svl_buf *ph = s <= 1 ? B0 : S2;
+        SVL_TRY(svl_launch_a_sweep(c, A.dt, A.kappa2, A.rho, A.H, A.psi, ph, B0, in, out, A.lang_c, A.rand_t, noise,
+                                   c->d_resid + s));
+    }
+    return 0;
+}
+
+extern "C" int svl_td_a_solve(svl_ctx *c, double dt, double kappa2, double rho, double H, const svl_buf *psi,
+                              svl_buf *ab, double lang_c, uint32_t rand_t, double stop_eps, int *sweeps_out) {
+    SVL_REQUIRE(c, "null context");
+    SVL_REQUIRE(psi && psi->kind == SVL_NODE_C, "psi must be SVL_NODE_C");
+    SVL_REQUIRE(ab && ab->kind == SVL_EDGE, "ab must be SVL_EDGE");
+    svl_buf *S1, *S2;
+    SVL_TRY(svl_scratch_edge(c, 0, &S1));
+    SVL_TRY(svl_scratch_edge(c, 1, &S2));
+    ASolveArgs A = {dt, kappa2, rho, H, psi, lang_c, rand_t};
+    SVL_CHECK(cudaMemsetAsync(c->d_resid, 0, SVL_MAX_SWEEPS * sizeof(unsigned long long), c->stream));
+    int done = 0, nstop = -1;
+    int pred = c->pred_A;
+    if (pred > SVL_MAX_SWEEPS) pred = SVL_MAX_SWEEPS;
+    while (nstop < 0) {
+        int upto = done == 0 && pred > 0 ? pred : done + 1;
+        if (upto > SVL_MAX_SWEEPS) upto = SVL_MAX_SWEEPS;
+        SVL_TRY(a_launch_range(c, A, ab, S1, S2, done, upto));
+        SVL_TRY(read_resid(c, done, upto - done));
+        for (int s = done; s < upto; s++)
+            if (stop_rule(c, slot_value(c->h_resid[s]), stop_eps)) { nstop = s + 1; break; }
+        done = upto;
+        if (nstop < 0 && done >= SVL_MAX_SWEEPS) nstop = SVL_MAX_SWEEPS;
+    }
+    if (nstop < done - 1) {   // overshoot by more than one: replay (an overshoot by one leaves in(done-1) intact)
+        c->stat_replays += 1;
+        SVL_TRY(a_launch_range(c, A, ab, S1, S2, 0, nstop));
+    }
+    svl_buf *res = ((nstop - 1) & 1) ? S2 : S1;
+    SVL_TRY(svl_swap(c, ab, res));
+    c->pred_A = nstop;
+    c->stat_A_sweeps += nstop;
+    if (sweeps_out) *sweeps_out = nstop;
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- outer loop
+extern "C" int svl_td_run(svl_ctx *c, int Nt, double dt, int solveA, double eps, const svl_buf *epsf, double kappa2,
+                          double rho, double H, svl_buf *psi, svl_buf *ab, double lang_psi, double lang_A,
+                          uint32_t *rand_t, double stop_psi, double stop_A, long long *sweeps) {
+    SVL_REQUIRE(c && rand_t, "null argument");
+    for (int t = 0; t < Nt; t++) {
+        int n = 0;
+        SVL_TRY(svl_td_psi_solve(c, dt, eps, epsf, ab, psi, lang_psi, *rand_t, stop_psi, &n));
+        *rand_t += 1u;                       // td.py:204
+        if (sweeps) sweeps[0] += n;
+        if (solveA) {
+            SVL_TRY(svl_td_a_solve(c, dt, kappa2, rho, H, psi, ab, lang_A, *rand_t, stop_A, &n));
+            *rand_t += 1u;                   // td.py:313
+            if (sweeps) sweeps[1] += n;
+        }
+    }
+    return 0;
+}

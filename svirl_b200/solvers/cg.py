@@ -1,0 +1,162 @@
+"""Modified nonlinear conjugate-gradient minimiser (API of svirl/solvers/cg.py:12-558).
+
+Device work per iteration is two library calls (svl_cg_begin: Jacobians, PR+ beta, direction
+update, line-search coefficients; svl_cg_end: variable update + free energy); the line search
+itself stays on the host and is the reference's numpy/scipy call, unchanged, because the
+trajectory depends on it bit by bit (cg.py:227-235, 378-419).
+
+State that persists across cg() calls exactly as in the reference (quirk Q6): beta_psi,
+beta_A and, for finite kappa, the search directions."""
+import ctypes as C
+
+import numpy as np
+import scipy.optimize
+
+import svirl_b200.config as cfg
+from svirl_b200 import _lib
+from svirl_b200.storage.arrays import DeviceArray
+
+
+def _h(x):
+    return x.handle if hasattr(x, 'handle') else None
+
+
+class CG(object):
+
+    def __init__(self, par, mesh, _vars, params, observables):
+        self.par = par
+        self.mesh = mesh
+        self.vars = _vars
+        self.params = params
+        self.fixed_vortices = self.params.fixed_vortices
+        self.observables = observables
+        self.__convergence_rtol = cfg.convergence_rtol
+        solveA = self.params.solveA
+        self.__reduction_vector_length = 17 if solveA else 5
+        Z = lambda kind: DeviceArray.zeros(par, kind)
+        self.__gdir_psi, self.__gjac_psi, self.__gjac_psi_prev = Z(_lib.NODE_C), Z(_lib.NODE_C), Z(_lib.NODE_C)
+        self._beta_psi = 0.0
+        self._beta_A = 0.0
+        if solveA:
+            self.__gdir_A, self.__gjac_A, self.__gjac_A_prev = Z(_lib.EDGE), Z(_lib.EDGE), Z(_lib.EDGE)
+        self.__c = np.zeros((5, 5), dtype=cfg.dtype) if solveA else np.zeros(5, dtype=cfg.dtype)
+        self.cg_energies = []
+
+    # ---- argument helpers
+    def _state(self):
+        p = self.params
+        self.vars._psi.sync()
+        if self.vars._vp is not None:
+            self.vars._vp.sync()
+        eps = float(np.asarray(p.linear_coefficient_scalar_h()).reshape(-1)[0])
+        return dict(k2=float(p.gl_parameter_squared_h()), eps=eps, epsf=_h(p.linear_coefficient_h()),
+                    H=float(p.homogeneous_external_field), psi=self.vars.order_parameter_h().handle,
+                    abei=_h(p.external_irregular_vector_potential_h()), ab=_h(self.vars.vector_potential_h()))
+
+    # ---- kernel-level private API used by the reference's tests
+    @property
+    def _free_energy_jacobian_psi(self):
+        """dG/dRe(psi) + i dG/dIm(psi) as a flat device array (cg.py:112-146)."""
+        s = self._state()
+        _lib.call("svl_jacobian_psi", self.par.ctx, s['k2'], s['eps'], s['epsf'], s['H'], s['psi'], s['abei'],
+                  s['ab'], self.__gjac_psi.handle)
+        return self.__gjac_psi
+
+    @property
+    def _free_energy_jacobian_A(self):
+        """[dG/da, dG/db] as a flat device array (cg.py:149-181); None for infinite kappa."""
+        if not self.params.solveA:
+            return None
+        s = self._state()
+        _lib.call("svl_jacobian_A", self.par.ctx, s['k2'], s['H'], s['psi'], s['abei'], s['ab'],
+                  self.__gjac_A.handle)
+        return self.__gjac_A
+
+    def _free_energy_conjgrad_coef_psi(self, gdir_psi):
+        """c0..c4 of G(psi + alpha*dpsi) (cg.py:184-224)."""
+        s = self._state()
+        out = (C.c_double * 5)()
+        _lib.call("svl_cg_coef_psi", self.par.ctx, s['k2'], s['eps'], s['H'], s['psi'], gdir_psi.handle,
+                  s['abei'], s['ab'], out)
+        self.__c[:] = np.array(out[:], dtype=cfg.dtype)     # broadcasts into every row of a 5x5 c, as in the reference
+        return self.__c
+
+    def _free_energy_conjgrad_coef(self, gdir_psi, gdir_A):
+        """c[i,j] of G(psi + a_psi*dpsi, A + a_A*dA), 4th order in a_A (cg.py:325-375)."""
+        s = self._state()
+        out = (C.c_double * 17)()
+        _lib.call("svl_cg_coef", self.par.ctx, s['k2'], s['eps'], s['H'], s['psi'], gdir_psi.handle,
+                  s['abei'], s['ab'], gdir_A.handle, out)
+        self._store_c17(np.array(out[:], dtype=cfg.dtype))
+        return self.__c
+
+    def _store_c17(self, r):
+        c = self.__c
+        c[0, :], c[1, :], c[2, :] = r[0:5], r[5:10], r[10:15]
+        c[3, 0], c[4, 0] = r[15], r[16]
+
+    # ---- host line searches: the reference's calls, verbatim in behaviour
+    def _cg_alpha_psi_min(self):
+        c = self.__c
+        am = np.polynomial.polynomial.polyroots([c[1], 2.0 * c[2], 3.0 * c[3], 4.0 * c[4]])
+        am = am[np.isclose(am.imag, 0)].real
+        am = am[am >= 0]
+        return np.min(am)
+
+    def _cg_alpha_min(self, alpha0=[0.0, 0.0], tol=1e-8):
+        c = self.__c
+        P = np.polynomial.polynomial
+        cj0 = P.polyder(c, axis=0)
+        cj1 = P.polyder(c, axis=1)
+
+        def f(alpha):
+            return P.polyval2d(alpha[0], alpha[1], c)
+
+        def j(alpha):
+            alpha_psi, alpha_A = alpha
+            return np.array([P.polyval2d(alpha_psi, alpha_A, cj0), P.polyval2d(alpha_psi, alpha_A, cj1)])
+
+        r = scipy.optimize.minimize(f, x0=np.array(alpha0), jac=j, method='BFGS', tol=tol)
+        return r.x
+
+    # ---- the two minimisation loops
+    def _iterate(self, n_iter, solveA):
+        s = self._state()
+        ctx = self.par.ctx
+        self.cg_energies = []
+        nul = None
+        gA, gAp, dA = ((self.__gjac_A, self.__gjac_A_prev, self.__gdir_A) if solveA else (nul, nul, nul))
+        if not solveA:
+            self.__gdir_psi.fill(0.0)            # the kappa=inf loop restarts from steepest descent (cg.py:264)
+        beta = (C.c_double * 2)(self._beta_psi, self._beta_A)
+        ncoef = 17 if solveA else 5
+        cbuf = (C.c_double * ncoef)()
+        E = C.c_double()
+        for i in range(n_iter):
+            _lib.call("svl_cg_begin", ctx, int(solveA), int(i > 0), s['k2'], s['eps'], s['epsf'], s['H'], s['psi'],
+                      s['abei'], s['ab'], self.__gjac_psi.handle, self.__gjac_psi_prev.handle,
+                      self.__gdir_psi.handle, _h(gA), _h(gAp), _h(dA), beta, cbuf)
+            r = np.array(cbuf[:], dtype=cfg.dtype)
+            if solveA:
+                self._store_c17(r)
+                alpha_psi, alpha_A = self._cg_alpha_min()
+            else:
+                self.__c[:] = r
+                alpha_psi, alpha_A = self._cg_alpha_psi_min(), 0.0
+            _lib.call("svl_cg_end", ctx, int(solveA), s['k2'], s['eps'], s['epsf'], s['H'], s['psi'], s['abei'],
+                      s['ab'], self.__gdir_psi.handle, _h(dA), float(cfg.dtype(alpha_psi)),
+                      float(cfg.dtype(alpha_A)), C.byref(E))
+            # "save previous gradient": swap storage instead of the reference's device copy
+            self.__gjac_psi.swap(self.__gjac_psi_prev)
+            if solveA:
+                self.__gjac_A.swap(self.__gjac_A_prev)
+            self.cg_energies.append(cfg.dtype(E.value))
+            if i > 0 and np.abs(self.cg_energies[i] / self.cg_energies[i - 1] - 1.0) < self.__convergence_rtol:
+                break
+        self._beta_psi, self._beta_A = beta[0], beta[1]
+        self.vars._psi.need_dtoh_sync()
+        if solveA:
+            self.vars._vp.need_dtoh_sync()
+
+    def _solve(self, n_iter=1000):
+        self._iterate(n_iter, bool(self.params.solveA))

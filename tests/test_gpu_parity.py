@@ -1,0 +1,237 @@
+"""GPU: the CUDA path (through GLSolver and the C ABI) against the reference's outputs stored in
+tests/golden (made from the unmodified reference, see oracle/make_golden.py) and against the
+NumPy oracle on the same seeded inputs.  Tolerances: fp64 1e-10 relative, fp32 1e-4."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, golden_inputs, has_cuda
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")]
+
+TD_CASES = ["td_f64_k5", "td_f64_k2_tiled_eps", "td_f64_kinf", "td_f64_k3_langevin",
+            "td_f32_kinf_tiled", "td_f32_k2_tiled_eps", "td_f32_k3_langevin"]
+
+
+def make_solver(m, d, **extra):
+    from svirl_b200 import GLSolver
+    kw = {k: v for k, v in m.items() if k not in ("Nt", "dtype")}
+    kw["dtype"] = np.dtype(m["dtype"]).type
+    if "mt" in d:
+        kw["material_tiling"] = d["mt"]
+    if "eps" in d and d["eps"].size > 1:
+        kw["linear_coefficient"] = d["eps"]
+    kw.update(extra)
+    return GLSolver(**kw)
+
+
+def relerr(x, ref):
+    return np.abs(x - ref).max() / max(np.abs(ref).max(), 1e-300)
+
+
+@pytest.mark.parametrize("kernel", [0])
+@pytest.mark.parametrize("name", TD_CASES)
+def test_td_trajectory(name, kernel):
+    d = load_golden(name)
+    m = d["meta"]
+    f64 = m["dtype"] == "float64"
+    gl = make_solver(m, d)
+    gl.par.set_option("psi_kernel", kernel)
+    assert np.array_equal(gl.vars.order_parameter, d["psi0"])
+    a0, b0 = gl.vars.vector_potential
+    assert np.array_equal(a0, d["a0"]) and np.array_equal(b0, d["b0"])
+    gl.solve.td(dt=0.1, Nt=m["Nt"])
+    psi = gl.vars.order_parameter
+    a, b = gl.vars.vector_potential
+    td = gl.solve._td
+    tol = 1e-10 if f64 else 1e-4
+    if f64:
+        assert (td.sweeps_order_parameter, td.sweeps_vector_potential) == (int(d["sweeps_psi"]), int(d["sweeps_A"]))
+    else:
+        assert abs(td.sweeps_order_parameter - int(d["sweeps_psi"])) <= 0.05 * int(d["sweeps_psi"])
+    assert int(td._random_t) == int(d["rand_t"])
+    assert relerr(psi, d["psi1"]) < tol
+    assert relerr(a, d["a1"]) < tol and relerr(b, d["b1"]) < tol
+    # observables of the end state
+    E = gl.observables.free_energy
+    assert abs(E - d["obs_E"]) < (1e-10 if f64 else 1e-4) * abs(d["obs_E"])
+    assert relerr(gl.observables.magnetic_field, d["obs_B"]) < (1e-9 if f64 else 1e-3)
+    jsx, jsy = gl.observables.supercurrent_density
+    atol = (1e-10 if f64 else 1e-4) * max(np.abs(d["obs_jsx"]).max(), 1e-3)
+    assert np.abs(jsx - d["obs_jsx"]).max() < atol and np.abs(jsy - d["obs_jsy"]).max() < atol
+    if "obs_jx" in d:
+        jx, jy = gl.observables.current_density
+        s = max(np.abs(d["obs_jx"]).max(), 1e-3)
+        assert np.abs(jx - d["obs_jx"]).max() < (1e-9 if f64 else 2e-3) * s
+        assert np.abs(jy - d["obs_jy"]).max() < (1e-9 if f64 else 2e-3) * s
+    vx, vy, vv = gl.vortex_detector.vortices
+    assert vx.size == d["obs_vx"].size and np.array_equal(vv, d["obs_vv"])
+    if f64:
+        assert np.allclose(vx, d["obs_vx"], rtol=0, atol=1e-8) and np.allclose(vy, d["obs_vy"], rtol=0, atol=1e-8)
+
+
+def _set_state(gl, d, psi_key="psi", a_key="a", b_key="b"):
+    gl.vars.order_parameter = d[psi_key]
+    gl.vars.vector_potential = (d[a_key], d[b_key])
+    gl.params.external_vector_potential = (d["ae"], d["be"])
+
+
+@pytest.mark.parametrize("name", ["kernels_f64_k3_ext", "kernels_f64_kinf", "kernels_f32_k3_ext", "kernels_f32_kinf"])
+def test_kernels(name):
+    from svirl_b200 import GLSolver
+    from svirl_b200.storage import GArray
+    d = load_golden(name)
+    dtype = d["a"].dtype.type
+    f64 = dtype is np.float64
+    Nx, Ny = d["psi"].shape
+    finite = "coef17" in d
+    kw = dict(Nx=Nx, Ny=Ny, dx=0.5, dy=0.4, dtype=dtype, homogeneous_external_field=float(d["H"]),
+              gl_parameter=float(np.sqrt(d["kappa2"])) if finite else np.inf)
+    if "mt" in d:
+        kw["material_tiling"] = d["mt"]
+    if bool(d["eps_is_field"]):
+        kw["linear_coefficient"] = d["eps"]
+    gl = GLSolver(**kw)
+    # kappa2 must be bit-identical to the fixture's
+    if finite:
+        assert gl.params.gl_parameter_squared_h() == pytest.approx(float(d["kappa2"]), rel=1e-6 if not f64 else 1e-14)
+    _set_state(gl, d)
+    tol = 1e-12 if f64 else 2e-5
+    E = gl.observables.free_energy
+    assert abs(E - d["E"]) < tol * abs(d["E"])
+    gl.solve._init_cg()
+    cg = gl.solve._cg
+    jp = gl.unflatten_array(cg._free_energy_jacobian_psi.get())
+    assert relerr(jp, d["jac_psi"]) < tol
+    dpsi = GArray(like=d["dpsi"])
+    if finite:
+        jA = cg._free_energy_jacobian_A.get()
+        ja, jb = gl.unflatten_a_array(jA[:gl.cfg.Na]), gl.unflatten_b_array(jA[gl.cfg.Na:])
+        s = max(np.abs(d["jac_a"]).max(), np.abs(d["jac_b"]).max())
+        assert np.abs(ja - d["jac_a"]).max() < 10 * tol * s and np.abs(jb - d["jac_b"]).max() < 10 * tol * s
+        dab = GArray(shape=[d["da"].shape, d["db"].shape], dtype=dtype)
+        dab.set_vec_h(d["da"], d["db"])
+        dab.sync()
+        c = np.array(cg._free_energy_conjgrad_coef(dpsi.get_d_obj(), dab.get_d_obj()))
+        assert relerr(c, d["coef17"]) < tol
+    c5 = np.array(cg._free_energy_conjgrad_coef_psi(dpsi.get_d_obj()))
+    c5 = c5[0, :] if c5.ndim == 2 else c5
+    assert relerr(c5, d["coef5"]) < tol
+
+
+@pytest.mark.parametrize("name", ["cg_f64_kinf", "cg_f32_kinf_tiled"])
+def test_cg_psi_trajectory(name):
+    from svirl_b200 import GLSolver
+    d = load_golden(name)
+    dtype = d["a0"].dtype.type
+    f64 = dtype is np.float64
+    Nx, Ny = d["psi0"].shape
+    kw = dict(Nx=Nx, Ny=Ny, dx=0.5, dy=0.4, dtype=dtype, homogeneous_external_field=float(d["H"]))
+    if "mt" in d:
+        kw["material_tiling"] = d["mt"]
+    gl = GLSolver(**kw)
+    _set_state(gl, d, "psi0", "a0", "b0")
+    gl.solve.cg(n_iter=25)
+    E1 = np.array(gl.solve._cg.cg_energies)
+    if f64:
+        assert len(E1) == len(d["E1"]) and np.allclose(E1, d["E1"], rtol=1e-10)
+        assert relerr(gl.vars.order_parameter, d["psi1"]) < 1e-9
+        gl.solve.cg(n_iter=5)
+        assert np.allclose(gl.solve._cg.cg_energies, d["E2"], rtol=1e-10)
+        assert relerr(gl.vars.order_parameter, d["psi2"]) < 1e-9
+    else:
+        n = min(len(E1), len(d["E1"]))
+        assert np.allclose(E1[:n], d["E1"][:n], rtol=2e-3)
+
+
+@pytest.mark.parametrize("name", ["cg_f64_k2", "cg_f64_k2_tiled_eps"])
+def test_cg_full_first_iterations(name):
+    """Finite kappa: SciPy BFGS turns 1e-15 coefficient noise into ~1e-9 alpha noise after a few
+    iterations (see tests/test_oracle_golden.py), so only the first iterations are tight."""
+    from svirl_b200 import GLSolver
+    d = load_golden(name)
+    Nx, Ny = d["psi0"].shape
+    kw = dict(Nx=Nx, Ny=Ny, dx=0.5, dy=0.4, homogeneous_external_field=float(d["H"]),
+              gl_parameter=float(d["kappa"]), normal_conductivity=10.0)
+    if "mt" in d:
+        kw["material_tiling"] = d["mt"]
+    if bool(d["eps_is_field"]):
+        kw["linear_coefficient"] = d["eps"]
+    gl = GLSolver(**kw)
+    _set_state(gl, d, "psi0", "a0", "b0")
+    gl.solve.cg(n_iter=8)
+    E = np.array(gl.solve._cg.cg_energies)
+    assert np.allclose(E[:3], d["E1"][:3], rtol=1e-9)
+    assert np.allclose(E, d["E1"][:len(E)], rtol=1e-3)
+    assert np.all(np.diff(E) < 0)          # energy decreases monotonically
+
+
+def test_cfg1_readme_1000_steps():
+    """BASELINE configs[0]: 129^2, kappa 5, sigma 200, H 0.1, fp64, td(0.1, 1000): psi, a, b within
+    1e-10, identical sweep counts, identical vortex count and positions."""
+    from svirl_b200 import GLSolver
+    d200, d1000 = load_golden("cfg1_td200"), load_golden("cfg1_td1000")
+    gl = GLSolver(Lx=64, Ly=64, dx=0.5, dy=0.5, gl_parameter=5.0, normal_conductivity=200.0,
+                  homogeneous_external_field=0.1, random_seed=1234)
+    assert np.array_equal(gl.vars.order_parameter, d200["psi0"])
+    gl.solve.td(dt=0.1, Nt=200)
+    td = gl.solve._td
+    assert (td.sweeps_order_parameter, td.sweeps_vector_potential) == (int(d200["sweeps_psi"]), int(d200["sweeps_A"]))
+    assert relerr(gl.vars.order_parameter, d200["psi1"]) < 1e-10
+    gl.solve.td(dt=0.1, Nt=800)
+    assert (td.sweeps_order_parameter, td.sweeps_vector_potential) == (int(d1000["sweeps_psi"]), int(d1000["sweeps_A"]))
+    a, b = gl.vars.vector_potential
+    assert relerr(gl.vars.order_parameter, d1000["psi1"]) < 1e-10
+    assert relerr(a, d1000["a1"]) < 1e-10 and relerr(b, d1000["b1"]) < 1e-10
+    assert abs(gl.observables.free_energy - d1000["obs_E"]) < 1e-10 * abs(d1000["obs_E"])
+    vx, vy, vv = gl.vortex_detector.vortices
+    assert vx.size == d1000["obs_vx"].size == 57
+    assert np.array_equal(vv, d1000["obs_vv"])
+    assert np.allclose(vx, d1000["obs_vx"], rtol=0, atol=1e-8) and np.allclose(vy, d1000["obs_vy"], rtol=0, atol=1e-8)
+
+
+def test_reductions_like_reference_at_reduction():
+    """tests/at_reduction.py of the reference: gsum / gsum_v against np.sum, atol 1e-10."""
+    from svirl_b200 import GLSolver
+    gl = GLSolver(Nx=16, Ny=16, dx=0.5, dy=0.5)
+    rs = np.random.RandomState(5)
+    for N in [1, 2, 31, 32, 33, 1000, 4097, 1234567]:
+        a = rs.rand(N)
+        assert abs(gl.par.red.test_sum(a, N, block_size=128) - a.sum()) < 1e-10 * max(N, 1)
+        v = rs.rand(N, 5)
+        out = gl.par.red.test_sum_v(v, N, 5, block_size=128)
+        assert np.allclose(out, v.sum(axis=0), rtol=0, atol=1e-10 * max(N, 1))
+
+
+def test_kernel_level_sweeps_match_oracle():
+    """svl_td_psi_sweep / svl_td_a_sweep (the kernel-level entry points) against one oracle sweep."""
+    import ctypes as C
+    import glnumpy as O
+    from svirl_b200 import GLSolver, _lib
+    from svirl_b200.storage.arrays import DeviceArray
+    d = load_golden("td_f64_k2_tiled_eps")
+    m = d["meta"]
+    gl = make_solver(m, d)
+    g = O.Grid(m["Nx"], m["Ny"], m["dx"], m["dy"], np.float64)
+    mt, eps = golden_inputs(d)
+    psi0, a0, b0 = d["psi1"], d["a1"], d["b1"]
+    gl.vars.order_parameter = psi0
+    gl.vars.vector_potential = (a0, b0)
+    par = gl.par
+    rhs = gl.vars._psi.get_d_obj().copy()
+    out = DeviceArray.zeros(par, _lib.NODE_C)
+    r = C.c_double()
+    _lib.call("svl_td_psi_sweep", par.ctx, 0.1, 0.0, gl.params.linear_coefficient_h().handle,
+              gl.vars.vector_potential_h().handle, rhs.handle, gl.vars.order_parameter_h().handle, out.handle,
+              0.0, 0, 1, C.byref(r))
+    nxt, ro, _ = O.psi_sweep(g, 0.1, eps, mt, a0, b0, psi0, psi0)
+    got = gl.unflatten_array(out.get())
+    assert np.abs(got - nxt).max() < 1e-14 and abs(r.value - ro) < 1e-15
+    ab = gl.vars.vector_potential_h()
+    rhs_e, out_e = ab.copy(), DeviceArray.zeros(par, _lib.EDGE)
+    _lib.call("svl_td_a_sweep", par.ctx, 0.1, 4.0, 0.1, 0.1, gl.vars.order_parameter_h().handle, ab.handle,
+              rhs_e.handle, ab.handle, out_e.handle, 0.0, 0, 1, C.byref(r))
+    an, bn, ro, _, _ = O.a_sweep(g, 0.1, 4.0, 0.1, 0.1, mt, psi0, a0, b0, a0, b0, a0, b0)
+    flat = out_e.get()
+    assert np.abs(gl.unflatten_a_array(flat[:gl.cfg.Na]) - an).max() < 1e-14
+    assert np.abs(gl.unflatten_b_array(flat[gl.cfg.Na:]) - bn).max() < 1e-14
+    assert abs(r.value - ro) < 1e-15
