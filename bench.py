@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the TDGL hot path (BASELINE.json metric: TDGL cell-steps/s, % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3]
+
+Workload at N=1 (BASELINE.json configs[1], SURVEY.md section 8d "cfg2"): infinite-kappa TDGL
+(psi only), 2048^2 nodes, fp32, dx=dy=0.5, dt=0.1, H=0.1, eps=1, seed 1234, material tiling =
+square lattice (period 16) of circular holes of radius 2.  A "step" is one TDGL time step = one
+complete psi Jacobi solve (about 20 sweeps) over the whole grid.
+
+One JSON line on stdout (rank 0).  `value` = nodes * steps / device time with the fields resident
+in HBM; `e2e` = the same through the C ABI with HOST buffers (pinned psi up, one step, psi down,
+every step); `roofline` = algorithmic bytes of the psi sweep kernel / its launch time vs the
+measured HBM copy peak; `cpu_baseline` = the reference's own kernel source compiled for the host
+cores (oracle/_ref, kind "reference") or the NumPy port, on a bounded sample.
+
+--impl reference times that CPU arm alone (the reference has no CPU path and pyCUDA cannot be
+installed offline).  With --gpus N > 1 (launched under torchrun) the grid is ...
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "tdgl_cell_steps_per_s"
+UNIT = "cell-steps/s"
+
+
+# ------------------------------------------------------------------------------------ workload
+def workload(name):
+    if name == "cfg2":
+        return dict(name="cfg2: TDGL kappa=inf 2048^2 fp32, hole-lattice tiling", Nx=2048, Ny=2048, dtype=np.float32,
+                    kappa=np.inf, sigma=1.0, H=0.1, tiling=True, eps_field=False)
+    if name == "cfg3":
+        return dict(name="cfg3: TDGL kappa=2 8192^2 fp64, disordered eps", Nx=8192, Ny=8192, dtype=np.float64,
+                    kappa=2.0, sigma=10.0, H=0.1, tiling=False, eps_field=True)
+    if name == "cfg1":
+        return dict(name="cfg1: README 129^2 fp64 kappa=5", Nx=129, Ny=129, dtype=np.float64, kappa=5.0, sigma=200.0,
+                    H=0.1, tiling=False, eps_field=False)
+    if name == "small":
+        return dict(name="small: 512^2 fp32 kappa=inf tiled", Nx=512, Ny=512, dtype=np.float32, kappa=np.inf,
+                    sigma=1.0, H=0.1, tiling=True, eps_field=False)
+    raise SystemExit("unknown workload " + name)
+
+
+def hole_tiling(Nx, Ny, dx=0.5, dy=0.5):
+    x = (np.arange(Nx - 1) + 0.5) * dx
+    y = (np.arange(Ny - 1) + 0.5) * dy
+    fx = (np.mod(x, 16.0) - 8.0) ** 2
+    fy = (np.mod(y, 16.0) - 8.0) ** 2
+    return ~((fx[:, None] + fy[None, :]) < 4.0)
+
+
+def make_solver(wl, device_id=0):
+    from svirl_b200 import GLSolver
+    kw = dict(Nx=wl["Nx"], Ny=wl["Ny"], dx=0.5, dy=0.5, dtype=wl["dtype"], gl_parameter=wl["kappa"],
+              normal_conductivity=wl["sigma"], homogeneous_external_field=wl["H"], random_seed=1234,
+              device_id=device_id)
+    if wl["tiling"]:
+        kw["material_tiling"] = hole_tiling(wl["Nx"], wl["Ny"])
+    if wl["eps_field"]:
+        kw["linear_coefficient"] = (0.7 + 0.3 * np.random.RandomState(4321).rand(wl["Nx"], wl["Ny"])).astype(wl["dtype"])
+    return GLSolver(**kw)
+
+
+def bytes_per_node_sweep(wl):
+    """psi node-sweep 8R+1(+R); A node-sweep 9R+1."""
+    R = np.dtype(wl["dtype"]).itemsize
+    psi = 8 * R + 1 + (R if wl["eps_field"] else 0)
+    return psi, 9 * R + 1
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=10)
+        sm, reasons, mx = [], set(), None
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = float(s[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU reference arm
+def _ref_lib(wl):
+    """oracle/_ref: the reference's kernel sources compiled for host cores (built by oracle/build_ref.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import build_ref
+    rvl = 5 if np.isinf(wl["kappa"]) else 17
+    path = os.path.join(build_ref.OUT, build_ref.prebuilt_name(wl["dtype"], wl["Nx"], wl["Ny"], 0.5, 0.5, rvl))
+    if not os.path.exists(path) and os.path.isdir(build_ref.REF_CUDA):
+        path = build_ref.prebuild(wl["dtype"], wl["Nx"], wl["Ny"], 0.5, 0.5, rvl)
+    return path if os.path.exists(path) else None
+
+
+def cpu_reference_steps(wl, nsteps, warmup=0):
+    """Time `nsteps` TDGL steps of the psi equation on the host cores.  Uses the reference kernel
+    (oracle/_ref .so) driven with the reference's launch pattern (svirl/solvers/td.py:157-218) when
+    it was built, else the NumPy port.  Returns (cell_steps_per_s, info)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import glnumpy as O
+    Nx, Ny, dt_ = wl["Nx"], wl["Ny"], wl["dtype"]
+    g = O.Grid(Nx, Ny, 0.5, 0.5, dt_)
+    psi = O.initial_psi(g, 1.0, 1234)
+    a, b = O.initial_A(g, wl["H"])
+    mt = hole_tiling(Nx, Ny) if wl["tiling"] else None
+    eps = (0.7 + 0.3 * np.random.RandomState(4321).rand(Nx, Ny)).astype(dt_) if wl["eps_field"] else 1.0
+    N = Nx * Ny
+    so = _ref_lib(wl)
+    sweeps = 0
+    if so is None:
+        t0 = time.perf_counter()
+        for s in range(warmup + nsteps):
+            if s == warmup:
+                t0 = time.perf_counter()
+                sweeps = 0
+            psi, n = O.td_psi_solve(g, 0.1, eps, mt, a, b, psi)
+            sweeps += n
+        el = time.perf_counter() - t0
+        return N * nsteps / el, dict(kind="port", cores=1, sweeps=sweeps, seconds=el)
+    lib = C.CDLL(so)
+    fn = lib.simt_launch_iterate_order_parameter_jacobi_step
+    real = C.c_float if dt_ is np.float32 else C.c_double
+    cplx = np.complex64 if dt_ is np.float32 else np.complex128
+    fn.argtypes = [C.c_int] * 4 + [real, real, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    real, C.c_uint32, C.c_uint32, real, C.c_void_p]
+    fn.restype = None
+    flat = lambda x: np.ascontiguousarray(np.reshape(x.T, x.size))
+    cur = flat(psi).astype(cplx)
+    nxt = np.zeros_like(cur)
+    rhs = np.zeros_like(cur)
+    ab = np.concatenate([flat(a), flat(b)]).astype(dt_)
+    mtf = flat(mt).astype(np.bool_) if mt is not None else None
+    epsf = flat(eps).astype(dt_) if wl["eps_field"] else None
+    r2 = np.zeros(1, dtype=np.int32)
+    grid = (N + 127) // 128
+    P = lambda x: x.ctypes.data if x is not None else None
+    t0 = time.perf_counter()
+    for s in range(warmup + nsteps):
+        if s == warmup:
+            t0 = time.perf_counter()
+            sweeps = 0
+        rhs[:] = cur
+        for j in range(1024):
+            r2[0] = 0
+            fn(grid, 1, 128, 0, 0.1, 0.0 if wl["eps_field"] else 1.0, P(epsf), P(mtf), P(ab), P(rhs), P(cur), P(nxt),
+               0.0, j, 1, 1e-6, P(r2))
+            cur, nxt = nxt, cur
+            sweeps += 1
+            if 1.0e-4 * float(r2[0]) < 1.0:
+                break
+    el = time.perf_counter() - t0
+    return N * nsteps / el, dict(kind="reference", cores=os.cpu_count(), sweeps=sweeps, seconds=el)
+
+
+# ------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--psi-kernel", type=int, default=None)
+    ap.add_argument("--psi-k", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = workload(args.workload)
+    N = wl["Nx"] * wl["Ny"]
+    cfgd = {"workload": wl["name"], "Nx": wl["Nx"], "Ny": wl["Ny"], "dt": 0.1, "seed": 1234,
+            "l2": "working set (3 psi planes + a,b + flags) exceeds the 126 MB L2" if N >= 2048 * 2048 else
+                  "working set fits in L2 (small-grid latency case)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        v, info = cpu_reference_steps(wl, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * info["seconds"] / max(args.steps, 1),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if wl["dtype"] is np.float32 else "f64", "data": "synthetic", "config": cfgd,
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+                                 "sample": "%d full-grid TDGL steps (%d Jacobi sweeps)" % (args.steps, info["sweeps"])},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+
+    from svirl_b200 import _lib
+    gl = make_solver(wl, device_id=local)
+    par = gl.par
+    if args.psi_kernel is not None:
+        par.set_option("psi_kernel", args.psi_kernel)
+    if args.psi_k is not None:
+        par.set_option("psi_k", args.psi_k)
+    td_kw = dict(dt=0.1)
+
+    def barrier():
+        par.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also settles the sweep-count prediction), then K timed steps
+    gl.solve.td(Nt=args.warmup, **td_kw)
+    td = gl.solve._td
+    barrier()
+    s0 = (td.sweeps_order_parameter, td.sweeps_vector_potential)
+    l0 = par.stat("launches")
+    sampler = ClockSampler(local)
+    sampler.start()
+    _lib.call("svl_event_record", par.ctx, 0)
+    gl.solve.td(Nt=args.steps, **td_kw)
+    _lib.call("svl_event_record", par.ctx, 1)
+    ms = C.c_double()
+    _lib.call("svl_event_elapsed_ms", par.ctx, 0, 1, C.byref(ms))
+    barrier()
+    clocks = sampler.stop()
+    launches = par.stat("launches") - l0
+    sw_psi = td.sweeps_order_parameter - s0[0]
+    sw_A = td.sweeps_vector_potential - s0[1]
+    t_ms = ms.value
+    if world > 1:
+        t = torch.tensor([t_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ms = float(t.item())
+    value = world * N * args.steps / (t_ms * 1e-3)
+
+    # ---- end to end through the C ABI with HOST buffers: psi up, one step, psi down, every step
+    cdt = np.complex64 if wl["dtype"] is np.float32 else np.complex128
+    pin_in = torch.empty(N * 2, dtype=torch.float32 if wl["dtype"] is np.float32 else torch.float64).pin_memory()
+    pin_out = torch.empty_like(pin_in).pin_memory()
+    h_in, h_out = pin_in.numpy().view(cdt), pin_out.numpy().view(cdt)
+    h_in[:] = gl.vars._psi.get_d_obj().get()
+    psi_h = gl.vars.order_parameter_h().handle
+    e2e_steps = max(3, min(args.steps, 20))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _lib.call("svl_h2d", par.ctx, psi_h, h_in.ctypes.data_as(C.c_void_p))
+        gl.solve.td(Nt=1, **td_kw)
+        _lib.call("svl_d2h", par.ctx, h_out.ctypes.data_as(C.c_void_p), psi_h)
+        h_in, h_out = h_out, h_in
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = world * N * e2e_steps / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (psi Jacobi sweep)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    bpsi, bA = bytes_per_node_sweep(wl)
+    alg_bytes = (sw_psi * bpsi + sw_A * bA) * N
+    achieved = alg_bytes / (t_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650",
+            "kernel": "psi Jacobi sweep", "bytes_per_node_sweep": bpsi, "sweeps_psi": int(sw_psi),
+            "sweeps_A": int(sw_A), "launches": int(launches),
+            "avg_launch_us": 1e3 * t_ms / max(launches, 1)}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        nst = 2 if N >= 2048 * 2048 else 5
+        v, info = cpu_reference_steps(wl, nst, 0)
+        cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+               "sample": "%d full-grid TDGL steps from the seeded initial state (%d Jacobi sweeps, %.1f s)"
+                         % (nst, info["sweeps"], info["seconds"])}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if wl["dtype"] is np.float32 else "f64", "data": "synthetic", "config": cfgd,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(N * np.dtype(cdt).itemsize),
+                    "d2h_bytes_per_step": int(N * np.dtype(cdt).itemsize), "steps": e2e_steps},
+            "gpu_launches": int(launches), "replays": par.stat("replays"),
+            "psi_kernel": int(args.psi_kernel) if args.psi_kernel is not None else None}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

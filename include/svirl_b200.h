@@ -57,6 +57,9 @@ int svl_synchronize(svl_ctx *ctx);
  * fused per launch), "tma" (0/1), "graphs" (0/1) */
 int svl_set_option(svl_ctx *ctx, const char *name, int value);
 int svl_get_stat(svl_ctx *ctx, const char *name, double *value);
+/* CUDA events on the context's launch stream (8 slots), for device-side timing */
+int svl_event_record(svl_ctx *ctx, int slot);
+int svl_event_elapsed_ms(svl_ctx *ctx, int slot0, int slot1, double *ms);
 
 /* ---- buffers: replaces pycuda.gpuarray + cuda.memcpy_* (svirl/storage/arrays.py:520-587,
  * svirl/parallel/utils.py:21-27).  n is only used for SVL_FLAT. */

@@ -84,6 +84,7 @@ extern "C" int svl_create(svl_ctx **out, int device_id, int Nx, int Ny, double d
     SVL_CHECK(cudaMalloc(&c->d_counter, 16 * sizeof(unsigned int)));
     SVL_CHECK(cudaMemsetAsync(c->d_counter, 0, 16 * sizeof(unsigned int), c->stream));
     SVL_CHECK(cudaMalloc(&c->d_ncand, sizeof(unsigned long long)));
+    for (int k = 0; k < 8; k++) SVL_CHECK(cudaEventCreate(&c->ev[k]));
     c->opt_psi_kernel = 0;
     c->opt_psi_k = 4;
     c->opt_tma = 1;
@@ -105,6 +106,7 @@ extern "C" int svl_destroy(svl_ctx *c) {
     cudaFree(c->nf); cudaFree(c->d_result); cudaFreeHost(c->h_result);
     cudaFree(c->d_resid); cudaFreeHost(c->h_resid); cudaFree(c->d_counter);
     cudaFree(c->partials); cudaFree(c->d_cand); cudaFree(c->d_candv); cudaFree(c->d_ncand);
+    for (int k = 0; k < 8; k++) cudaEventDestroy(c->ev[k]);
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -113,6 +115,23 @@ extern "C" int svl_destroy(svl_ctx *c) {
 extern "C" int svl_synchronize(svl_ctx *c) {
     SVL_REQUIRE(c, "null context");
     SVL_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// CUDA events on the stream every kernel of this context is launched on (torch.cuda.Event would
+// only see torch's current stream).
+extern "C" int svl_event_record(svl_ctx *c, int slot) {
+    SVL_REQUIRE(c && slot >= 0 && slot < 8, "bad event slot");
+    SVL_CHECK(cudaEventRecord(c->ev[slot], c->stream));
+    return 0;
+}
+
+extern "C" int svl_event_elapsed_ms(svl_ctx *c, int slot0, int slot1, double *ms) {
+    SVL_REQUIRE(c && ms && slot0 >= 0 && slot0 < 8 && slot1 >= 0 && slot1 < 8, "bad event slot");
+    SVL_CHECK(cudaEventSynchronize(c->ev[slot1]));
+    float f = 0.f;
+    SVL_CHECK(cudaEventElapsedTime(&f, c->ev[slot0], c->ev[slot1]));
+    *ms = (double)f;
     return 0;
 }
 

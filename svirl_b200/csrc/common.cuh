@@ -92,6 +92,7 @@ struct svl_ctx {
     int opt_psi_kernel, opt_psi_k, opt_tma, opt_graphs;
     int pred_psi, pred_A;          // predicted sweep counts (from the previous time step)
     double stat_launches, stat_replays, stat_psi_sweeps, stat_A_sweeps;
+    cudaEvent_t ev[8];
 };
 
 static inline int svl_nblocks(size_t n, int b) { return (int)((n + b - 1) / b); }

@@ -269,19 +269,35 @@ struct PsiSolveArgs {
     double dt, eps; const svl_buf *epsf; const svl_buf *ab; double lang_c; uint32_t rand_t;
 };
 
-static int psi_launch_range(svl_ctx *c, const PsiSolveArgs &A, svl_buf *B0, svl_buf *S1, svl_buf *S2, int s0, int s1) {
-    // sweeps [s0, s1); uses the temporally blocked kernel for runs of K sweeps when enabled
+// Buffer rotation state: `cur` holds the newest iterate, the next launch writes to S[toggle].
+struct PsiIter {
+    svl_buf *B0, *S[2];
+    svl_buf *cur, *prev;
+    int toggle;
+    int lastK;
+    void reset() { cur = B0; prev = nullptr; toggle = 0; lastK = 0; }
+};
+
+// Launch sweeps [s0, s1).  With the temporally blocked kernel, runs of up to psi_k sweeps go into
+// one launch; tail_single keeps the final sweep in a launch of its own so that the iterate before
+// it survives (an overshoot by one sweep then costs nothing).
+static int psi_launch_range(svl_ctx *c, const PsiSolveArgs &A, PsiIter &it, int s0, int s1, bool tail_single) {
     int s = s0;
     while (s < s1) {
-        const svl_buf *in = s == 0 ? B0 : ((s & 1) ? S1 : S2);
         int K = 1;
-        if (c->opt_psi_kernel == 1) { K = c->opt_psi_k; if (K > s1 - s) K = s1 - s; }
-        svl_buf *out = ((s + K - 1) & 1) ? S2 : S1;      // out(s + K - 1)
         if (c->opt_psi_kernel == 1) {
-            SVL_TRY(svl_launch_psi_stream(c, K, A.dt, A.eps, A.epsf, A.ab, B0, in, out, A.lang_c, A.rand_t, c->d_resid + s));
-        } else {
-            SVL_TRY(svl_launch_psi_sweep(c, A.dt, A.eps, A.epsf, A.ab, B0, in, out, A.lang_c, A.rand_t, c->d_resid + s));
+            K = c->opt_psi_k;
+            int left = s1 - s;
+            if (tail_single && left > 1) left -= 1;
+            if (K > left) K = left;
         }
+        svl_buf *out = it.S[it.toggle];
+        if (c->opt_psi_kernel == 1) {
+            SVL_TRY(svl_launch_psi_stream(c, K, A.dt, A.eps, A.epsf, A.ab, it.B0, it.cur, out, A.lang_c, A.rand_t, c->d_resid + s));
+        } else {
+            SVL_TRY(svl_launch_psi_sweep(c, A.dt, A.eps, A.epsf, A.ab, it.B0, it.cur, out, A.lang_c, A.rand_t, c->d_resid + s));
+        }
+        it.prev = it.cur; it.cur = out; it.toggle ^= 1; it.lastK = K;
         s += K;
     }
     return 0;
@@ -291,9 +307,11 @@ extern "C" int svl_td_psi_solve(svl_ctx *c, double dt, double eps, const svl_buf
                                 svl_buf *psi, double lang_c, uint32_t rand_t, double stop_eps, int *sweeps_out) {
     SVL_REQUIRE(c, "null context");
     SVL_TRY(check_kinds(psi, ab, epsf));
-    svl_buf *S1, *S2;
-    SVL_TRY(svl_scratch_node(c, 0, &S1));
-    SVL_TRY(svl_scratch_node(c, 1, &S2));
+    PsiIter it;
+    it.B0 = psi;
+    SVL_TRY(svl_scratch_node(c, 0, &it.S[0]));
+    SVL_TRY(svl_scratch_node(c, 1, &it.S[1]));
+    it.reset();
     PsiSolveArgs A = {dt, eps, epsf, ab, lang_c, rand_t};
     SVL_CHECK(cudaMemsetAsync(c->d_resid, 0, SVL_MAX_SWEEPS * sizeof(unsigned long long), c->stream));
     int done = 0, nstop = -1;
@@ -302,25 +320,23 @@ extern "C" int svl_td_psi_solve(svl_ctx *c, double dt, double eps, const svl_buf
     while (nstop < 0) {
         int upto = done == 0 && pred > 0 ? pred : done + 1;
         if (upto > SVL_MAX_SWEEPS) upto = SVL_MAX_SWEEPS;
-        SVL_TRY(psi_launch_range(c, A, psi, S1, S2, done, upto));
+        SVL_TRY(psi_launch_range(c, A, it, done, upto, true));
         SVL_TRY(read_resid(c, done, upto - done));
         for (int s = done; s < upto; s++)
             if (stop_rule(c, slot_value(c->h_resid[s]), stop_eps)) { nstop = s + 1; break; }
         done = upto;
         if (nstop < 0 && done >= SVL_MAX_SWEEPS) nstop = SVL_MAX_SWEEPS;   // reference: loop exhausts, keeps last iterate
     }
-    // iterate nstop lives in out(nstop-1); `done` sweeps were executed
-    if (nstop < done) {
-        int lastK = 1;   // granularity of the final launch: result recoverable only at launch boundaries
-        if (nstop == done - 1 && !(c->opt_psi_kernel == 1 && c->opt_psi_k > 1)) {
-            // overshoot by one single sweep: the input of the last sweep is iterate nstop, still intact
-            (void)lastK;
-        } else {
-            c->stat_replays += 1;
-            SVL_TRY(psi_launch_range(c, A, psi, S1, S2, 0, nstop));
-        }
+    // `done` sweeps were executed; the reference stops after nstop <= done sweeps
+    svl_buf *res = it.cur;
+    if (nstop == done - 1 && it.lastK == 1 && it.prev != it.B0) {
+        res = it.prev;                       // iterate before the last single sweep is still intact
+    } else if (nstop < done) {
+        c->stat_replays += 1;
+        it.reset();
+        SVL_TRY(psi_launch_range(c, A, it, 0, nstop, false));
+        res = it.cur;
     }
-    svl_buf *res = ((nstop - 1) & 1) ? S2 : S1;
     SVL_TRY(svl_swap(c, psi, res));
     c->pred_psi = nstop;
     c->stat_psi_sweeps += nstop;

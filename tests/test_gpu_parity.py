@@ -28,14 +28,27 @@ def relerr(x, ref):
     return np.abs(x - ref).max() / max(np.abs(ref).max(), 1e-300)
 
 
-@pytest.mark.parametrize("kernel", [0])
+# psi-sweep kernel variants: plain per-node kernel, streaming kernel (TMA staging) at several
+# temporal-blocking depths, and the streaming kernel with plain-load staging
+KERNELS = [("plain", 0, 1, 1), ("stream_k4_tma", 1, 4, 1), ("stream_k1_tma", 1, 1, 1), ("stream_k3_tma", 1, 3, 1),
+           ("stream_k6_tma", 1, 6, 1), ("stream_k4_ldg", 1, 4, 0)]
+
+
+def set_kernel(gl, kernel):
+    _, pk, k, tma = kernel
+    gl.par.set_option("psi_kernel", pk)
+    gl.par.set_option("psi_k", k)
+    gl.par.set_option("tma", tma)
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=[k[0] for k in KERNELS])
 @pytest.mark.parametrize("name", TD_CASES)
 def test_td_trajectory(name, kernel):
     d = load_golden(name)
     m = d["meta"]
     f64 = m["dtype"] == "float64"
     gl = make_solver(m, d)
-    gl.par.set_option("psi_kernel", kernel)
+    set_kernel(gl, kernel)
     assert np.array_equal(gl.vars.order_parameter, d["psi0"])
     a0, b0 = gl.vars.vector_potential
     assert np.array_equal(a0, d["a0"]) and np.array_equal(b0, d["b0"])
@@ -165,13 +178,15 @@ def test_cg_full_first_iterations(name):
     assert np.all(np.diff(E) < 0)          # energy decreases monotonically
 
 
-def test_cfg1_readme_1000_steps():
+@pytest.mark.parametrize("kernel", [KERNELS[0], KERNELS[1]], ids=["plain", "stream_k4_tma"])
+def test_cfg1_readme_1000_steps(kernel):
     """BASELINE configs[0]: 129^2, kappa 5, sigma 200, H 0.1, fp64, td(0.1, 1000): psi, a, b within
     1e-10, identical sweep counts, identical vortex count and positions."""
     from svirl_b200 import GLSolver
     d200, d1000 = load_golden("cfg1_td200"), load_golden("cfg1_td1000")
     gl = GLSolver(Lx=64, Ly=64, dx=0.5, dy=0.5, gl_parameter=5.0, normal_conductivity=200.0,
                   homogeneous_external_field=0.1, random_seed=1234)
+    set_kernel(gl, kernel)
     assert np.array_equal(gl.vars.order_parameter, d200["psi0"])
     gl.solve.td(dt=0.1, Nt=200)
     td = gl.solve._td
@@ -235,3 +250,28 @@ def test_kernel_level_sweeps_match_oracle():
     assert np.abs(gl.unflatten_a_array(flat[:gl.cfg.Na]) - an).max() < 1e-14
     assert np.abs(gl.unflatten_b_array(flat[gl.cfg.Na:]) - bn).max() < 1e-14
     assert abs(r.value - ro) < 1e-15
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_stream_kernel_equals_plain_kernel_large_grid(dtype):
+    """Size-independent property at a multi-strip, multi-segment size: the temporally blocked
+    streaming kernel and the plain kernel follow the same trajectory (same sweep counts; values
+    equal to rounding) on a 700 x 517 tiled grid with a disordered linear coefficient."""
+    from svirl_b200 import GLSolver
+    Nx, Ny = 700, 517
+    rs = np.random.RandomState(3)
+    mt = rs.rand(Nx - 1, Ny - 1) > 0.15
+    eps = (0.7 + 0.3 * rs.rand(Nx, Ny)).astype(dtype)
+    out = []
+    for kernel in (KERNELS[0], KERNELS[1], KERNELS[5], KERNELS[3]):
+        gl = GLSolver(Nx=Nx, Ny=Ny, dx=0.5, dy=0.5, dtype=dtype, homogeneous_external_field=0.1, random_seed=5,
+                      material_tiling=mt, linear_coefficient=eps)
+        set_kernel(gl, kernel)
+        gl.solve.td(dt=0.1, Nt=12)
+        out.append((gl.vars.order_parameter, gl.solve._td.sweeps_order_parameter))
+        gl.par.close()
+    tol = 1e-12 if dtype is np.float64 else 2e-5
+    for psi, n in out[1:]:
+        if dtype is np.float64:
+            assert n == out[0][1]
+        assert np.abs(psi - out[0][0]).max() < tol
