@@ -85,12 +85,11 @@ extern "C" int svl_create(svl_ctx **out, int device_id, int Nx, int Ny, double d
     SVL_CHECK(cudaMemsetAsync(c->d_counter, 0, 16 * sizeof(unsigned int), c->stream));
     SVL_CHECK(cudaMalloc(&c->d_ncand, sizeof(unsigned long long)));
     for (int k = 0; k < 8; k++) SVL_CHECK(cudaEventCreate(&c->ev[k]));
-    c->opt_psi_kernel = 0;
+    c->opt_psi_kernel = 2;
     c->opt_psi_k = 4;
     c->opt_tma = 1;
     c->opt_graphs = 1;
-    c->pred_psi = 0;
-    c->pred_A = 0;
+    c->pred_psi = c->pred_A = c->pred_psi2 = c->pred_A2 = 0;
     *out = c;
     return svl_set_material(c, nullptr);
 }
@@ -141,7 +140,7 @@ extern "C" int svl_set_option(svl_ctx *c, const char *name, int v) {
     else if (!strcmp(name, "psi_k")) { SVL_REQUIRE(v >= 1 && v <= SVL_HALO, "psi_k out of range"); c->opt_psi_k = v; }
     else if (!strcmp(name, "tma")) c->opt_tma = v;
     else if (!strcmp(name, "graphs")) c->opt_graphs = v;
-    else if (!strcmp(name, "reset_prediction")) { c->pred_psi = 0; c->pred_A = 0; }
+    else if (!strcmp(name, "reset_prediction")) { c->pred_psi = c->pred_A = c->pred_psi2 = c->pred_A2 = 0; }
     else { svl_set_error("unknown option %s", name); return 2; }
     return 0;
 }

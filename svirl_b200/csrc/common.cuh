@@ -51,6 +51,8 @@ struct Geo {
 template <typename R> struct V2;
 template <> struct V2<float>  { typedef float2 type; };
 template <> struct V2<double> { typedef double2 type; };
+__device__ __forceinline__ float fma_r(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_r(double a, double b, double c) { return fma(a, b, c); }
 
 // node flag bits (svirl/cuda/td.h:48-57)
 #define NF_MM 1
@@ -90,7 +92,8 @@ struct svl_ctx {
     long long *d_cand; double *d_candv; unsigned long long *d_ncand; size_t cand_cap;
     // options / stats
     int opt_psi_kernel, opt_psi_k, opt_tma, opt_graphs;
-    int pred_psi, pred_A;          // predicted sweep counts (from the previous time step)
+    int pred_psi, pred_A;          // sweep counts of the previous solve
+    int pred_psi2, pred_A2;        // ... and of the one before (trend)
     double stat_launches, stat_replays, stat_psi_sweeps, stat_A_sweeps;
     cudaEvent_t ev[8];
 };
@@ -114,8 +117,35 @@ int svl_scratch_edge(svl_ctx *c, int k, svl_buf **out);
 // ----------------------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
 template <typename R> __device__ __forceinline__ void sincos_r(R x, R *s, R *c);
-template <> __device__ __forceinline__ void sincos_r<float>(float x, float *s, float *c) { sincosf(x, s, c); }
+// fp32: branch-free Cody-Waite reduction (3-term pi/2) + minimax polynomials on [-pi/4, pi/4]
+// (max abs error 7.6e-8 ~ 1.3 ulp for |x| < 2e4, measured against double; same class as sincosf,
+// a third of its instructions).  Larger arguments take libdevice's sincosf.
+struct sc_f { float s, c; };
+static __device__ __noinline__ sc_f sincosf_slow(float x) { sc_f r; sincosf(x, &r.s, &r.c); return r; }
+template <> __device__ __forceinline__ void sincos_r<float>(float x, float *s, float *c) {
+    if (fabsf(x) > 20000.0f) { sc_f r = sincosf_slow(x); *s = r.s; *c = r.c; return; }   // out of line, by value
+    float j = rintf(x * 0.636619772f);
+    int q = __float2int_rn(j);
+    float r = fmaf(j, -1.5707962513e+0f, x);
+    r = fmaf(j, -7.5497894159e-08f, r);
+    r = fmaf(j, -5.3903029534e-15f, r);
+    float z = r * r;
+    float sp = fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f);
+    float sn = fmaf(sp * z, r, r);
+    float cp = fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f);
+    float cs = fmaf(cp * z, z, fmaf(-0.5f, z, 1.0f));
+    float s2 = (q & 1) ? cs : sn, c2 = (q & 1) ? sn : cs;
+    *s = (q & 2) ? -s2 : s2;
+    *c = ((q + 1) & 2) ? -c2 : c2;
+}
 template <> __device__ __forceinline__ void sincos_r<double>(double x, double *s, double *c) { sincos(x, s, c); }
+// 1/x for x of order 1 (the Jacobi diagonal): MUFU.RCP + one Newton step, ~1 ulp, no slow path
+__device__ __forceinline__ float rcp_r(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+__device__ __forceinline__ double rcp_r(double x) { return __drcp_rn(x); }
 
 // Thomas Wang hash RNG of the reference (svirl/cuda/common.h:36-63): exact integer maths.
 __device__ __forceinline__ uint32_t wang_hash(uint32_t s) {

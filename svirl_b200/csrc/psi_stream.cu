@@ -79,7 +79,7 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, in
 }
 
 // ------------------------------------------------------------------------------- shared memory plan
-template <typename R, int K, int EX, int RB, int NS>
+template <typename R, int K, int EX, int RB, int NS, bool EPS>
 struct StreamSmem {
     typedef typename V2<R>::type C;
     static constexpr int CD = 2 * K + 2;          // constants ring rows
@@ -92,9 +92,9 @@ struct StreamSmem {
     static constexpr size_t st_a = st_rhs + sizeof(C) * RB * EX;
     static constexpr size_t st_b = st_a + sizeof(R) * RB * EX;
     static constexpr size_t st_eps = st_b + sizeof(R) * RB * EX;
-    static constexpr size_t st_nf = st_eps + sizeof(R) * RB * EX;
+    static constexpr size_t st_nf = st_eps + (EPS ? sizeof(R) * RB * EX : 0);
     static constexpr size_t st_size = ((st_nf + RB * NFW + 127) / 128) * 128;
-    static constexpr uint32_t st_tx_bytes = (uint32_t)(2 * sizeof(C) * RB * EX + 3 * sizeof(R) * RB * EX + RB * NFW);
+    static constexpr uint32_t st_tx_bytes = (uint32_t)(2 * sizeof(C) * RB * EX + (EPS ? 3 : 2) * sizeof(R) * RB * EX + RB * NFW);
     static constexpr size_t off_stage = 0;
     static constexpr size_t off_q = off_stage + NS * st_size;
     static constexpr size_t off_la = off_q + sizeof(C) * CD * W;
@@ -102,21 +102,21 @@ struct StreamSmem {
     static constexpr size_t off_dinv = off_lb + sizeof(C) * CD * W;
     static constexpr size_t off_ring = ((off_dinv + sizeof(R) * CD * W + 15) / 16) * 16;
     static constexpr size_t off_bar = ((off_ring + sizeof(C) * K * PS_RD * W + 15) / 16) * 16;
-    static constexpr size_t total = off_bar + 8 * NS + 128;   // + slack for the 128-byte base alignment
+    static constexpr size_t total = off_bar + 8 * NS + 16;
 };
 
 // ------------------------------------------------------------------------------- the kernel
-template <typename R, int K, int EX, int RB, int NS, bool TMA>
+template <typename R, int K, int EX, int RB, int NS, bool TMA, bool EPS>
 __global__ void __launch_bounds__(EX)
 k_psi_stream(const __grid_constant__ StreamArgs A, const __grid_constant__ CUtensorMap tm_psi,
              const __grid_constant__ CUtensorMap tm_rhs, const __grid_constant__ CUtensorMap tm_a,
              const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_eps,
              const __grid_constant__ CUtensorMap tm_nf) {
     typedef typename V2<R>::type C;
-    typedef StreamSmem<R, K, EX, RB, NS> S;
+    typedef StreamSmem<R, K, EX, RB, NS, EPS> S;
     constexpr int CD = S::CD, W = S::W, H = S::H, NFW = S::NFW, TX = EX - 2 * H;
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    // declared alignment keeps the pointers in the shared address space (LDS/STS, not generic LD/ST)
+    extern __shared__ __align__(128) unsigned char smem[];
     C *q = (C *)(smem + S::off_q);
     C *la = (C *)(smem + S::off_la);
     C *lb = (C *)(smem + S::off_lb);
@@ -138,6 +138,7 @@ k_psi_stream(const __grid_constant__ StreamArgs A, const __grid_constant__ CUten
     const bool xin = (x >= 0 && x < g.Nx);
     const bool xout = (t >= H && t < EX - H && x < g.Nx);
     const R dt = (R)A.dt, dx = (R)g.dx, dy = (R)g.dy, idx2 = (R)g.idx2, idy2 = (R)g.idy2;
+    const R eps0 = (R)A.eps, lang = (R)A.lang_c;
     const R cx = dt * idx2, cy = dt * idy2;
     const int nchunks = (nin + RB - 1) / RB;
 
@@ -152,14 +153,13 @@ k_psi_stream(const __grid_constant__ StreamArgs A, const __grid_constant__ CUten
             if (t == 0) {
                 uint32_t bytes = S::st_tx_bytes;
                 if (A.same_rhs) bytes -= (uint32_t)(sizeof(C) * RB * EX);
-                if (!A.has_eps) bytes -= (uint32_t)(sizeof(R) * RB * EX);
                 mbar_expect_tx(&full[s], bytes);
                 const int cmul = sizeof(C) / 8 == 2 ? 2 : 1;     // complex double = two 8-byte elements
                 tma_load_2d(st + S::st_psi, &tm_psi, (x0 - H) * cmul, prow, &full[s]);
                 if (!A.same_rhs) tma_load_2d(st + S::st_rhs, &tm_rhs, (x0 - H) * cmul, prow, &full[s]);
                 tma_load_2d(st + S::st_a, &tm_a, x0 - H, prow, &full[s]);
                 tma_load_2d(st + S::st_b, &tm_b, x0 - H, prow, &full[s]);
-                if (A.has_eps) tma_load_2d(st + S::st_eps, &tm_eps, x0 - H, prow, &full[s]);
+                if (EPS) tma_load_2d(st + S::st_eps, &tm_eps, x0 - H, prow, &full[s]);
                 tma_load_2d(st + S::st_nf, &tm_nf, xs16, prow, &full[s]);
             }
         } else {
@@ -175,7 +175,7 @@ k_psi_stream(const __grid_constant__ StreamArgs A, const __grid_constant__ CUten
                 if (!A.same_rhs) ((C *)(st + S::st_rhs))[r * EX + t] = ok ? grhs[n] : z;
                 ((R *)(st + S::st_a))[r * EX + t] = ok ? ga[n] : (R)0;
                 ((R *)(st + S::st_b))[r * EX + t] = ok ? gb[n] : (R)0;
-                ((R *)(st + S::st_eps))[r * EX + t] = (ok && A.has_eps) ? ge[n] : (R)0;
+                if (EPS) ((R *)(st + S::st_eps))[r * EX + t] = ok ? ge[n] : (R)0;
                 (st + S::st_nf)[r * NFW + nfd + t] = ok ? A.nf[n] : (uint8_t)0;
             }
         }
@@ -194,10 +194,12 @@ k_psi_stream(const __grid_constant__ StreamArgs A, const __grid_constant__ CUten
 #pragma unroll
     for (int k = 0; k < K; k++) rmax[k] = 0;
 
+    int c0 = 0;                              // step mod CD, kept incrementally
+    int chunk = 0, ri = 0;                   // step / RB, step mod RB
     for (int step = 0; step < nsteps; step++) {
         // ---- arrival of input row `step`: constants + level-0 values
         if (step < nin) {
-            int chunk = step / RB, ri = step - chunk * RB, s = chunk % NS;
+            int s = chunk % NS;
             if (TMA && ri == 0) mbar_wait(&full[s], (uint32_t)((chunk / NS) & 1));
             unsigned char *st = stage_ptr(s);
             C p0 = ((const C *)(st + S::st_psi))[ri * EX + t];
@@ -205,7 +207,7 @@ k_psi_stream(const __grid_constant__ StreamArgs A, const __grid_constant__ CUten
             R av = ((const R *)(st + S::st_a))[ri * EX + t];
             R bv = ((const R *)(st + S::st_b))[ri * EX + t];
             unsigned f = (st + S::st_nf)[ri * NFW + nfd + t];
-            R e = A.has_eps ? ((const R *)(st + S::st_eps))[ri * EX + t] : (R)A.eps;
+            R e = EPS ? ((const R *)(st + S::st_eps))[ri * EX + t] : eps0;
             if (!xin) f = 0;
             C La, Lb;
             La.x = La.y = Lb.x = Lb.y = 0;
@@ -213,8 +215,8 @@ k_psi_stream(const __grid_constant__ StreamArgs A, const __grid_constant__ CUten
             if (f) {
                 if (A.noise) {
                     uint32_t nn = (uint32_t)x + (uint32_t)g.Nx * (uint32_t)(yb + step);
-                    qq.x += (R)A.lang_c * (rand_1<R>(nn, A.rand_t) - (R)0.5);
-                    qq.y += (R)A.lang_c * (rand_2<R>(nn, A.rand_t) - (R)0.5);
+                    qq.x += lang * (rand_1<R>(nn, A.rand_t) - (R)0.5);
+                    qq.y += lang * (rand_2<R>(nn, A.rand_t) - (R)0.5);
                 }
                 R sn, cs;
                 if (f & (NF_PM | NF_PP)) { sincos_r<R>(dx * av, &sn, &cs); La.x = cx * cs; La.y = cx * sn; }
@@ -222,11 +224,11 @@ k_psi_stream(const __grid_constant__ StreamArgs A, const __grid_constant__ CUten
                 int nwx = ((f & (NF_MM | NF_MP)) ? 1 : 0) + ((f & (NF_PM | NF_PP)) ? 1 : 0);
                 int nwy = ((f & (NF_MM | NF_PM)) ? 1 : 0) + ((f & (NF_MP | NF_PP)) ? 1 : 0);
                 R D = (R)1.0 + dt * (qq.x * qq.x + qq.y * qq.y - e + (idx2 * (R)nwx + idy2 * (R)nwy));
-                di = (R)1.0 / D;
+                di = rcp_r(D);
             } else {
                 qq.x = 0; qq.y = 0;
             }
-            int cs_ = step % CD;
+            int cs_ = c0;
             q[cs_ * W + t + 1] = qq;
             la[cs_ * W + t + 1] = La;
             lb[cs_ * W + t + 1] = Lb;
@@ -239,7 +241,9 @@ k_psi_stream(const __grid_constant__ StreamArgs A, const __grid_constant__ CUten
             int rk = step - 2 * k;
             if (rk >= k && rk <= nin - 1 - k) {
                 const C *src = ring + (size_t)(k - 1) * PS_RD * W;
-                int cs_ = rk % CD, csm = (rk - 1) % CD;
+                int cs_ = c0 - 2 * k;          // (step - 2k) mod CD
+                if (cs_ < 0) cs_ += CD;
+                int csm = cs_ == 0 ? CD - 1 : cs_ - 1;
                 int ps = (rk & (PS_RD - 1)) * W + t + 1;
                 int pm = ((rk - 1) & (PS_RD - 1)) * W + t + 1, pp = ((rk + 1) & (PS_RD - 1)) * W + t + 1;
                 C pw = src[ps - 1], pe = src[ps + 1], pS = src[pm], pN = src[pp], pc = src[ps];
@@ -262,10 +266,13 @@ k_psi_stream(const __grid_constant__ StreamArgs A, const __grid_constant__ CUten
             }
         }
         __syncthreads();
+        if (++c0 == CD) c0 = 0;
         // ---- refill the stage that was just drained
-        if ((step + 1) % RB == 0) {
-            int next = (step + 1) / RB - 1 + NS;
+        if (++ri == RB) {
+            ri = 0;
+            int next = chunk + NS;
             if (next < nchunks) issue_chunk(next);
+            chunk++;
         }
     }
     // ---- per-sweep max-norm updates -> one atomicMax per CTA and sweep
@@ -320,19 +327,19 @@ static int make_map(CUtensorMap *tm, CUtensorMapDataType dt, int esize, const vo
     return 0;
 }
 
-template <typename R, int K, int EX, int RB, int NS>
-static int launch_stream_t(svl_ctx *c, StreamArgs &A, bool tma) {
+template <typename R, int K, int EX, int RB, int NS, bool TMA, bool EPS>
+static int launch_stream_t(svl_ctx *c, StreamArgs &A) {
     typedef typename V2<R>::type C;
-    typedef StreamSmem<R, K, EX, RB, NS> S;
+    typedef StreamSmem<R, K, EX, RB, NS, EPS> S;
     const Geo &g = c->g;
     const int TX = EX - 2 * S::H;
     int nstrips = (g.Nx + TX - 1) / TX;
     int rows = g.j1 - g.j0;
+    auto kern = k_psi_stream<R, K, EX, RB, NS, TMA, EPS>;
     // one wave: (resident CTAs per SM) x (SM count) CTAs at most; segments of at least 32 rows
     size_t smem = S::total;
-    int occ = 1, nsm = 148;
-    {
-        auto kern = k_psi_stream<R, K, EX, RB, NS, true>;
+    static int occ = 0, nsm = 0;          // per instantiation
+    if (!occ) {
         SVL_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SVL_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, EX, smem));
         SVL_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
@@ -347,7 +354,7 @@ static int launch_stream_t(svl_ctx *c, StreamArgs &A, bool tma) {
     A.TY = TY;
     CUtensorMap tm[6];
     memset(tm, 0, sizeof(tm));
-    if (tma) {
+    if (TMA) {
         const bool dbl = sizeof(R) == 8;
         CUtensorMapDataType rt = dbl ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
         // complex float is moved as one 8-byte element, complex double as two 8-byte elements
@@ -358,36 +365,40 @@ static int launch_stream_t(svl_ctx *c, StreamArgs &A, bool tma) {
         SVL_TRY(make_map(&tm[1], ct, 8, A.rhs, (size_t)g.Nx * cmul, g.rows, pc, EX * cmul, RB));
         SVL_TRY(make_map(&tm[2], rt, sizeof(R), A.a, g.Nx, g.rows, pr, EX, RB));
         SVL_TRY(make_map(&tm[3], rt, sizeof(R), A.b, g.Nx, g.rows, pr, EX, RB));
-        SVL_TRY(make_map(&tm[4], rt, sizeof(R), A.has_eps ? A.epsf : A.a, g.Nx, g.rows, pr, EX, RB));
+        SVL_TRY(make_map(&tm[4], rt, sizeof(R), EPS ? A.epsf : A.a, g.Nx, g.rows, pr, EX, RB));
         SVL_TRY(make_map(&tm[5], CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, A.nf, g.Nx, g.rows, (size_t)g.P, S::NFW, RB));
     }
     dim3 grid(nstrips, nsegs);
-    if (tma) {
-        auto kern = k_psi_stream<R, K, EX, RB, NS, true>;
-        SVL_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, EX, smem, c->stream>>>(A, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]);
-    } else {
-        auto kern = k_psi_stream<R, K, EX, RB, NS, false>;
-        SVL_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, EX, smem, c->stream>>>(A, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]);
-    }
+    kern<<<grid, EX, smem, c->stream>>>(A, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]);
     SVL_CHECK(cudaGetLastError());
     c->stat_launches += 1;
     return 0;
 }
 
-template <typename R, int RB, int NS>
+template <typename R, int RB, int NS, bool EPS>
 static int launch_stream_k(svl_ctx *c, int K, StreamArgs &A, bool tma) {
-    switch (K) {
-        case 1: return launch_stream_t<R, 1, 128, RB, NS>(c, A, tma);
-        case 2: return launch_stream_t<R, 2, 128, RB, NS>(c, A, tma);
-        case 3: return launch_stream_t<R, 3, 128, RB, NS>(c, A, tma);
-        case 4: return launch_stream_t<R, 4, 128, RB, NS>(c, A, tma);
-        case 5: return launch_stream_t<R, 5, 128, RB, NS>(c, A, tma);
-        case 6: return launch_stream_t<R, 6, 128, RB, NS>(c, A, tma);
+    if (!tma) {
+        if (K == 4) return launch_stream_t<R, 4, 128, RB, NS, false, EPS>(c, A);
+        svl_set_error("psi_stream: the plain-load staging variant is built for K=4 only");
+        return 2;
     }
-    svl_set_error("psi_stream: K=%d not instantiated (1..6)", K);
+    switch (K) {
+        case 1: return launch_stream_t<R, 1, 128, RB, NS, true, EPS>(c, A);
+        case 2: return launch_stream_t<R, 2, 128, RB, NS, true, EPS>(c, A);
+        case 3: return launch_stream_t<R, 3, 128, RB, NS, true, EPS>(c, A);
+        case 4: return launch_stream_t<R, 4, 128, RB, NS, true, EPS>(c, A);
+        case 6: return launch_stream_t<R, 6, 128, RB, NS, true, EPS>(c, A);
+        case 8: return launch_stream_t<R, 8, 128, RB, NS, true, EPS>(c, A);
+    }
+    svl_set_error("psi_stream: K=%d not instantiated (1,2,3,4,6,8)", K);
     return 2;
+}
+
+// largest instantiated K that does not exceed the request (the solve driver chops sweep runs)
+int svl_psi_stream_fit_k(int K) {
+    static const int ks[] = {8, 6, 4, 3, 2, 1};
+    for (int k : ks) if (k <= K) return k;
+    return 1;
 }
 
 int svl_launch_psi_stream(svl_ctx *c, int K, double dt, double eps, const svl_buf *epsf, const svl_buf *ab,
@@ -404,6 +415,10 @@ int svl_launch_psi_stream(svl_ctx *c, int K, double dt, double eps, const svl_bu
     A.epsf = epsf ? epsf->p[0] : nullptr;
     A.nf = c->nf; A.out = out->p[0]; A.slots = resid_slots;
     bool tma = c->opt_tma != 0;
-    if (c->rsize == 4) return launch_stream_k<float, 4, 2>(c, K, A, tma);
-    return launch_stream_k<double, 2, 2>(c, K, A, tma);
+    if (c->rsize == 4) {
+        if (epsf) return launch_stream_k<float, 2, 2, true>(c, K, A, tma);
+        return launch_stream_k<float, 2, 2, false>(c, K, A, tma);
+    }
+    if (epsf) return launch_stream_k<double, 2, 2, true>(c, K, A, tma);
+    return launch_stream_k<double, 2, 2, false>(c, K, A, tma);
 }

@@ -1,0 +1,389 @@
+// Temporally blocked psi sweeps, register-resident variant: K sweeps per launch on an
+// overlapped 2-D tile (same arithmetic as k_psi_sweep in td.cu / svirl/cuda/td.h:5-133).
+//
+//   * a CTA loads an extended tile of TXE x EY nodes (interior + halo of H = roundup(K,4)
+//     columns / K rows) with one set of 2-D TMA boxes (psi, rhs, a, b, [eps], flags) into shared
+//     memory; zero fill outside the plane supplies the domain boundary;
+//   * each thread owns V consecutive rows of one column for all K sweeps.  Everything that is
+//     constant during the solve -- right-hand side, 1/diagonal and the two link coefficients
+//     w*dt/d^2*exp(-i d A) of its nodes (one sincos per link and launch) -- lives in REGISTERS;
+//     only the psi iterate goes through shared memory (double buffered, one __syncthreads per
+//     sweep), and only the W/E neighbours (+ the two strip ends) are read from it: about 3 shared
+//     loads and 1 shared store per node update instead of 11 + 1 in the streaming variant;
+//   * the halo shrinks by one ring per sweep; after K sweeps the interior is exact and is
+//     written back; the max-norm update of each of the K sweeps is reduced over the interior
+//     and merged with one atomicMax per CTA and sweep.
+// HBM traffic per launch: the one-sweep bytes times the halo overhead (1.3-1.5x), for K sweeps.
+#include "common.cuh"
+#include <cuda.h>
+
+struct TileArgs {
+    Geo g;
+    double dt, eps, lang_c;
+    uint32_t rand_t;
+    int noise;
+    int same_rhs;
+    void *out;
+    unsigned long long *slots;
+};
+
+__device__ __forceinline__ uint32_t t_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void t_tma_load_2d(void *dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(t_smem_u32(dst)), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(t_smem_u32(bar))
+        : "memory");
+}
+
+template <typename R, int K, int TXE, int V, int NB, bool EPS>
+struct TileSmem {
+    typedef typename V2<R>::type C;
+    static constexpr int EY = V * NB;
+    static constexpr int H = ((K + 3) / 4) * 4;
+    static constexpr int NFW = TXE + 16;
+    static constexpr int XW = TXE + 2;                  // exchange row width (zero pad column each side)
+    static constexpr int XR = EY + 2;                   // exchange rows (zero pad row each side)
+    // staging (TMA destinations, 128-byte aligned); refilled for the NEXT tile while this one is swept
+    static constexpr size_t st_psi = 0;
+    static constexpr size_t st_rhs = st_psi + sizeof(C) * EY * TXE;
+    static constexpr size_t st_a = st_rhs + sizeof(C) * EY * TXE;
+    static constexpr size_t st_b = st_a + sizeof(R) * EY * TXE;
+    static constexpr size_t st_eps = st_b + sizeof(R) * EY * TXE;
+    static constexpr size_t st_nf = st_eps + (EPS ? sizeof(R) * EY * TXE : 0);
+    static constexpr size_t st_end = ((st_nf + (size_t)EY * NFW + 127) / 128) * 128;
+    static constexpr uint32_t tx_bytes = (uint32_t)(2 * sizeof(C) * EY * TXE + (EPS ? 3 : 2) * sizeof(R) * EY * TXE + EY * NFW);
+    // psi exchange (double buffered) and the a-link coefficient tile (W coefficient of the right neighbour)
+    static constexpr size_t off_x0 = st_end;
+    static constexpr size_t off_x1 = off_x0 + sizeof(C) * XR * XW;
+    static constexpr size_t off_la = off_x1 + sizeof(C) * XR * XW;
+    static constexpr size_t off_bar = ((off_la + sizeof(C) * XR * XW + 15) / 16) * 16;
+    static constexpr size_t total = off_bar + 16;
+};
+
+// Persistent CTAs: each loops over tiles tile = blockIdx.x, +gridDim.x, ...; the TMA boxes of the
+// next tile are issued as soon as this tile's constants are in registers, so the load overlaps the
+// K sweeps.
+template <typename R, int K, int TXE, int V, int NB, bool EPS>
+__global__ void __launch_bounds__(TXE *NB, (sizeof(R) == 4 ? 2 : 1))
+k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorMap tm_psi,
+           const __grid_constant__ CUtensorMap tm_rhs, const __grid_constant__ CUtensorMap tm_a,
+           const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_eps,
+           const __grid_constant__ CUtensorMap tm_nf) {
+    typedef typename V2<R>::type C;
+    typedef TileSmem<R, K, TXE, V, NB, EPS> S;
+    constexpr int EY = S::EY, H = S::H, NFW = S::NFW, XW = S::XW, XR = S::XR;
+    constexpr int TX = TXE - 2 * H, TYO = EY - 2 * K, NT = TXE * NB;
+    extern __shared__ __align__(128) unsigned char smem[];
+    C *xb0 = (C *)(smem + S::off_x0);
+    C *xb1 = (C *)(smem + S::off_x1);
+    C *sla = (C *)(smem + S::off_la);
+    uint64_t *bar = (uint64_t *)(smem + S::off_bar);
+
+    const Geo &g = A.g;
+    const int tid = threadIdx.x;
+    const int col = tid % TXE, band = tid / TXE;
+    const int r0 = band * V;                             // first tile row of this thread
+    const int ntx = (g.Nx + TX - 1) / TX, nty = (g.j1 - g.j0 + TYO - 1) / TYO;
+    const int ntiles = ntx * nty;
+    const R dt = (R)A.dt, dx = (R)g.dx, dy = (R)g.dy, idx2 = (R)g.idx2, idy2 = (R)g.idy2;
+    const R cx = dt * idx2, cy = dt * idy2, eps0 = (R)A.eps, lang = (R)A.lang_c;
+
+    auto issue = [&](int tile) {                         // thread 0 only
+        const int bx = tile % ntx, by = tile / ntx;
+        const int xg0 = bx * TX - H, prow = g.j0 + by * TYO - K - g.rb;
+        const int xs16 = ((xg0 + 1024) / 16) * 16 - 1024;
+        uint32_t bytes = S::tx_bytes;
+        if (A.same_rhs) bytes -= (uint32_t)(sizeof(C) * EY * TXE);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(t_smem_u32(bar)), "r"(bytes) : "memory");
+        const int cmul = sizeof(C) / 8 == 2 ? 2 : 1;
+        t_tma_load_2d(smem + S::st_psi, &tm_psi, xg0 * cmul, prow, bar);
+        if (!A.same_rhs) t_tma_load_2d(smem + S::st_rhs, &tm_rhs, xg0 * cmul, prow, bar);
+        t_tma_load_2d(smem + S::st_a, &tm_a, xg0, prow, bar);
+        t_tma_load_2d(smem + S::st_b, &tm_b, xg0, prow, bar);
+        if (EPS) t_tma_load_2d(smem + S::st_eps, &tm_eps, xg0, prow, bar);
+        t_tma_load_2d(smem + S::st_nf, &tm_nf, xs16, prow, bar);
+    };
+
+    int tile = blockIdx.x;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(t_smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (tile < ntiles) issue(tile);
+    }
+    // zero the pad ring of the exchange / coefficient tiles once (never overwritten afterwards)
+    {
+        C z; z.x = 0; z.y = 0;
+        for (int i = tid; i < XW; i += NT) {
+            xb0[i] = z; xb1[i] = z; sla[i] = z;
+            xb0[(XR - 1) * XW + i] = z; xb1[(XR - 1) * XW + i] = z; sla[(XR - 1) * XW + i] = z;
+        }
+        for (int i = tid; i < XR; i += NT) {
+            xb0[i * XW] = z; xb1[i * XW] = z; sla[i * XW] = z;
+            xb0[i * XW + XW - 1] = z; xb1[i * XW + XW - 1] = z; sla[i * XW + XW - 1] = z;
+        }
+    }
+    __shared__ unsigned int sm_rmax[K];      // per-sweep max-norm update of this CTA (bit patterns of floats/doubles >= 0)
+    __shared__ unsigned long long sm_rmax64[K];
+    if (tid < K) { sm_rmax[tid] = 0u; sm_rmax64[tid] = 0ull; }
+    uint32_t phase = 0;
+
+    for (; tile < ntiles; tile += gridDim.x) {
+        const int bx = tile % ntx, by = tile / ntx;
+        const int xg0 = bx * TX - H;                     // global column of tile column 0
+        const int yg0 = g.j0 + by * TYO - K;             // global row of tile row 0
+        const int x = xg0 + col;
+        const int nfd = xg0 - (((xg0 + 1024) / 16) * 16 - 1024);
+        // ---- wait for this tile's boxes: one warp polls, the barrier releases the rest
+        if (tid < 32) {
+            uint32_t ok = 0;
+            for (uint32_t it = 0; !ok; it++) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(t_smem_u32(bar)), "r"(phase) : "memory");
+                if (it > (1u << 24)) __trap();           // broken descriptor: fail the launch, do not hang
+            }
+        }
+        phase ^= 1;
+        __syncthreads();      // also: everybody is done with the previous tile's exchange buffers
+
+        // ---- per-node constants into registers
+        C psi[V], q[V], La[V], Lb[V];
+        R di[V];
+        C LbS0;
+        LbS0.x = 0; LbS0.y = 0;
+        const bool xin = (x >= 0 && x < g.Nx);
+        if (r0 > 0) {         // S-link coefficient of the strip's first row = b-link of tile row r0-1
+            const int si = (r0 - 1) * TXE + col;
+            unsigned f = (smem + S::st_nf)[(r0 - 1) * NFW + nfd + col];
+            if (xin && (f & (NF_MP | NF_PP))) {
+                R sn, cs;
+                sincos_r<R>(dy * ((const R *)(smem + S::st_b))[si], &sn, &cs);
+                LbS0.x = cy * cs; LbS0.y = cy * sn;
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+            const int r = r0 + v, si = r * TXE + col;
+            C p0 = ((const C *)(smem + S::st_psi))[si];
+            C qq = A.same_rhs ? p0 : ((const C *)(smem + S::st_rhs))[si];
+            R av = ((const R *)(smem + S::st_a))[si], bv = ((const R *)(smem + S::st_b))[si];
+            unsigned f = (smem + S::st_nf)[r * NFW + nfd + col];
+            R e = EPS ? ((const R *)(smem + S::st_eps))[si] : eps0;
+            if (!xin) f = 0;
+            // branch-free: weights are 0/1 factors (inactive node: q = 0, links 0, 1/D irrelevant)
+            if (A.noise && f) {
+                uint32_t nn = (uint32_t)x + (uint32_t)g.Nx * (uint32_t)(yg0 + r);
+                qq.x += lang * (rand_1<R>(nn, A.rand_t) - (R)0.5);
+                qq.y += lang * (rand_2<R>(nn, A.rand_t) - (R)0.5);
+            }
+            const R wE = (f & (NF_PM | NF_PP)) ? cx : (R)0, wN = (f & (NF_MP | NF_PP)) ? cy : (R)0;
+            const R act = f ? (R)1 : (R)0;
+            R sn, cs;
+            C la, lb;
+            sincos_r<R>(dx * av, &sn, &cs); la.x = wE * cs; la.y = wE * sn;
+            sincos_r<R>(dy * bv, &sn, &cs); lb.x = wN * cs; lb.y = wN * sn;
+            const R nwx = ((f & (NF_MM | NF_MP)) ? (R)1 : (R)0) + ((f & (NF_PM | NF_PP)) ? (R)1 : (R)0);
+            const R nwy = ((f & (NF_MM | NF_PM)) ? (R)1 : (R)0) + ((f & (NF_MP | NF_PP)) ? (R)1 : (R)0);
+            qq.x *= act; qq.y *= act;
+            const R D = (R)1.0 + dt * (qq.x * qq.x + qq.y * qq.y - e + (idx2 * nwx + idy2 * nwy));
+            const R d = rcp_r(D);
+            psi[v] = p0; q[v] = qq; La[v] = la; Lb[v] = lb; di[v] = d;
+            const int xi = (r + 1) * XW + col + 1;
+            xb0[xi] = p0;
+            sla[xi] = la;
+        }
+        __syncthreads();      // staging fully consumed; level-0 values and a-link coefficients visible
+        if (tid == 0 && tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);   // prefetch overlaps the sweeps
+
+        const bool cin = (col >= H && col < TXE - H && x < g.Nx);
+        unsigned inmask = 0;                  // bit v: node v of this thread is an output node of the tile
+#pragma unroll
+        for (int v = 0; v < V; v++)
+            if (cin && r0 + v >= K && r0 + v < EY - K && yg0 + r0 + v < g.j1) inmask |= 1u << v;
+        const C *src = xb0;
+        C *dst = xb1;
+#pragma unroll 1
+        for (int k = 0; k < K; k++) {          // rolled on purpose: the unrolled body would not fit the instruction cache
+            R rm = 0;
+            C nx[V];
+            const C below = src[(r0) * XW + col + 1];              // tile row r0-1
+            const C above = src[(r0 + V + 1) * XW + col + 1];      // tile row r0+V
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+                const int xi = (r0 + v + 1) * XW + col + 1;
+                const C pw = src[xi - 1], pe = src[xi + 1];
+                const C lw = sla[xi - 1];
+                const C pS = v > 0 ? psi[v - 1] : below;
+                const C pN = v < V - 1 ? psi[v + 1] : above;
+                const C ls = v > 0 ? Lb[v - 1] : LbS0;
+                // 16 chained FMAs: W,S use (c + i s) psi, E,N use (c - i s) psi
+                R ax = q[v].x, ay = q[v].y;
+                ax = fma_r(lw.x, pw.x, ax);     ay = fma_r(lw.x, pw.y, ay);
+                ax = fma_r(-lw.y, pw.y, ax);    ay = fma_r(lw.y, pw.x, ay);
+                ax = fma_r(La[v].x, pe.x, ax);  ay = fma_r(La[v].x, pe.y, ay);
+                ax = fma_r(La[v].y, pe.y, ax);  ay = fma_r(-La[v].y, pe.x, ay);
+                ax = fma_r(ls.x, pS.x, ax);     ay = fma_r(ls.x, pS.y, ay);
+                ax = fma_r(-ls.y, pS.y, ax);    ay = fma_r(ls.y, pS.x, ay);
+                ax = fma_r(Lb[v].x, pN.x, ax);  ay = fma_r(Lb[v].x, pN.y, ay);
+                ax = fma_r(Lb[v].y, pN.y, ax);  ay = fma_r(-Lb[v].y, pN.x, ay);
+                nx[v].x = ax * di[v];
+                nx[v].y = ay * di[v];
+            }
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+                const int r = r0 + v;
+                if (inmask & (1u << v))
+                    rm = fmax(rm, fmax(fabs(nx[v].x - psi[v].x), fabs(nx[v].y - psi[v].y)));
+                psi[v] = nx[v];
+                if (k < K - 1) dst[(r + 1) * XW + col + 1] = nx[v];
+            }
+            // warp max -> one shared atomicMax per warp and sweep (non-negative values order like their bits)
+            for (int o = 16; o > 0; o >>= 1) rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, o));
+            if ((tid & 31) == 0 && rm > (R)0) {
+                if (sizeof(R) == 4) atomicMax(&sm_rmax[k], __float_as_uint((float)rm));
+                else atomicMax(&sm_rmax64[k], (unsigned long long)__double_as_longlong((double)rm));
+            }
+            if (k < K - 1) __syncthreads();
+            const C *tsw = src; src = dst; dst = (C *)tsw;
+        }
+        // ---- write the interior
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+            if (inmask & (1u << v)) ((C *)A.out)[g.at(x, yg0 + r0 + v)] = psi[v];
+        }
+    }
+    // ---- per-sweep max-norm updates -> one global atomicMax per CTA and sweep
+    __syncthreads();
+    if (tid < K) {
+        double r = sizeof(R) == 4 ? (double)__uint_as_float(sm_rmax[tid]) : __longlong_as_double((long long)sm_rmax64[tid]);
+        if (r > 0.0) atomicMax(A.slots + tid, (unsigned long long)__double_as_longlong(r));
+    }
+}
+
+// ------------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled t_get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+static int t_make_map(CUtensorMap *tm, CUtensorMapDataType dt, const void *base, size_t width, size_t rows,
+                      size_t pitch_bytes, int box_w, int box_h) {
+    PFN_encodeTiled enc = t_get_encode();
+    SVL_REQUIRE(enc, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(tm, dt, 2, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        svl_set_error("cuTensorMapEncodeTiled failed: %d (width %zu rows %zu pitch %zu box %dx%d)", (int)r, width, rows,
+                      pitch_bytes, box_w, box_h);
+        return 1;
+    }
+    return 0;
+}
+
+struct TileIO {
+    const void *psi, *rhs, *a, *b, *epsf;
+    const uint8_t *nf;
+};
+
+// Tensor maps depend only on (base pointer, geometry, box): the three psi buffers rotate, so a
+// small cache avoids six driver encode calls per launch.
+struct MapKey { const void *base; int w, rows, box_w, box_h, dt; size_t pitch; };
+struct MapEnt { MapKey k; CUtensorMap tm; };
+static int cached_map(CUtensorMap *out, CUtensorMapDataType dt, const void *base, size_t width, size_t rows,
+                      size_t pitch_bytes, int box_w, int box_h) {
+    static MapEnt cache[64];
+    static int n = 0, next = 0;
+    MapKey k = {base, (int)width, (int)rows, box_w, box_h, (int)dt, pitch_bytes};
+    for (int i = 0; i < n; i++)
+        if (!memcmp(&cache[i].k, &k, sizeof(k))) { *out = cache[i].tm; return 0; }
+    CUtensorMap tm;
+    SVL_TRY(t_make_map(&tm, dt, base, width, rows, pitch_bytes, box_w, box_h));
+    int slot = n < 64 ? n++ : (next++ % 64);
+    memset(&cache[slot].k, 0, sizeof(MapKey));
+    cache[slot].k = k; cache[slot].tm = tm;
+    *out = tm;
+    return 0;
+}
+
+template <typename R, int K, int TXE, int V, int NB, bool EPS>
+static int launch_tile_t(svl_ctx *c, TileArgs &A, const TileIO &io) {
+    typedef typename V2<R>::type C;
+    typedef TileSmem<R, K, TXE, V, NB, EPS> S;
+    const Geo &g = c->g;
+    constexpr int TX = TXE - 2 * S::H, TYO = S::EY - 2 * K;
+    static_assert(TYO > 0 && TX > 0, "tile too small for this K");
+    auto kern = k_psi_tile<R, K, TXE, V, NB, EPS>;
+    static int slots = 0;
+    if (!slots) {
+        int occ = 1, nsm = 148;
+        SVL_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total));
+        SVL_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TXE * NB, S::total));
+        SVL_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
+        slots = (occ < 1 ? 1 : occ) * nsm;
+    }
+    const bool dbl = sizeof(R) == 8;
+    CUtensorMapDataType rt = dbl ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUtensorMapDataType ct = CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    const int cmul = dbl ? 2 : 1;
+    static_assert(TXE * 2 <= 256, "complex double box exceeds 256 elements");
+    size_t pr = (size_t)g.P * sizeof(R), pc = (size_t)g.P * sizeof(C);
+    CUtensorMap tm[6];
+    SVL_TRY(cached_map(&tm[0], ct, io.psi, (size_t)g.Nx * cmul, g.rows, pc, TXE * cmul, S::EY));
+    SVL_TRY(cached_map(&tm[1], ct, io.rhs, (size_t)g.Nx * cmul, g.rows, pc, TXE * cmul, S::EY));
+    SVL_TRY(cached_map(&tm[2], rt, io.a, g.Nx, g.rows, pr, TXE, S::EY));
+    SVL_TRY(cached_map(&tm[3], rt, io.b, g.Nx, g.rows, pr, TXE, S::EY));
+    SVL_TRY(cached_map(&tm[4], rt, EPS ? io.epsf : io.a, g.Nx, g.rows, pr, TXE, S::EY));
+    SVL_TRY(cached_map(&tm[5], CU_TENSOR_MAP_DATA_TYPE_UINT8, io.nf, g.Nx, g.rows, (size_t)g.P, S::NFW, S::EY));
+    int ntiles = ((g.Nx + TX - 1) / TX) * ((g.j1 - g.j0 + TYO - 1) / TYO);
+    int grid = ntiles < slots ? ntiles : slots;
+    kern<<<grid, TXE * NB, S::total, c->stream>>>(A, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]);
+    SVL_CHECK(cudaGetLastError());
+    c->stat_launches += 1;
+    return 0;
+}
+
+template <typename R, int TXE, int V, int NB, bool EPS>
+static int launch_tile_k(svl_ctx *c, int K, TileArgs &A, const TileIO &io) {
+    switch (K) {
+        case 1: return launch_tile_t<R, 1, TXE, V, NB, EPS>(c, A, io);
+        case 2: return launch_tile_t<R, 2, TXE, V, NB, EPS>(c, A, io);
+        case 3: return launch_tile_t<R, 3, TXE, V, NB, EPS>(c, A, io);
+        case 4: return launch_tile_t<R, 4, TXE, V, NB, EPS>(c, A, io);
+        case 6: return launch_tile_t<R, 6, TXE, V, NB, EPS>(c, A, io);
+        case 8: return launch_tile_t<R, 8, TXE, V, NB, EPS>(c, A, io);
+    }
+    svl_set_error("psi_tile: K=%d not instantiated (1,2,3,4,6,8)", K);
+    return 2;
+}
+
+int svl_launch_psi_tile(svl_ctx *c, int K, double dt, double eps, const svl_buf *epsf, const svl_buf *ab,
+                        const svl_buf *rhs, const svl_buf *psi, svl_buf *out, double lang_c, uint32_t rand_t,
+                        unsigned long long *resid_slots) {
+    TileArgs A;
+    memset(&A, 0, sizeof(A));
+    A.g = c->g;
+    A.dt = dt; A.eps = eps; A.lang_c = lang_c; A.rand_t = rand_t;
+    A.noise = lang_c > 1.0e-32 ? 1 : 0;
+    A.same_rhs = rhs->p[0] == psi->p[0];
+    A.out = out->p[0]; A.slots = resid_slots;
+    TileIO io = {psi->p[0], rhs->p[0], ab->p[0], ab->p[1], epsf ? epsf->p[0] : nullptr, c->nf};
+    if (c->rsize == 4) {
+        if (epsf) return launch_tile_k<float, 64, 8, 4, true>(c, K, A, io);
+        return launch_tile_k<float, 64, 8, 4, false>(c, K, A, io);
+    }
+    if (epsf) return launch_tile_k<double, 64, 4, 8, true>(c, K, A, io);
+    return launch_tile_k<double, 64, 4, 8, false>(c, K, A, io);
+}

@@ -6,6 +6,10 @@
 int svl_launch_psi_stream(svl_ctx *c, int K, double dt, double eps, const svl_buf *epsf, const svl_buf *ab,
                           const svl_buf *rhs, const svl_buf *psi, svl_buf *out, double lang_c, uint32_t rand_t,
                           unsigned long long *resid_slots);   // psi_stream.cu
+int svl_psi_stream_fit_k(int K);
+int svl_launch_psi_tile(svl_ctx *c, int K, double dt, double eps, const svl_buf *epsf, const svl_buf *ab,
+                        const svl_buf *rhs, const svl_buf *psi, svl_buf *out, double lang_c, uint32_t rand_t,
+                        unsigned long long *resid_slots);     // psi_tile.cu
 
 // ----------------------------------------------------------------------------- plain psi sweep
 // One thread per node; neighbours come through L1/L2.  NOISE: 0 none, 1 add + write back to rhs
@@ -111,6 +115,8 @@ k_a_sweep(Geo g, R dt, R kappa2, R rho, R H, const uint8_t *__restrict__ nf,
     const R dx = (R)g.dx, dy = (R)g.dy, idx = (R)g.idx, idy = (R)g.idy, idx2 = (R)g.idx2, idy2 = (R)g.idy2,
             idxy = (R)g.idxy;
     const R dt_rho = dt * rho, dtrk = dt_rho * kappa2;
+    // the Jacobi diagonals are constants: multiply by their reciprocals (<= 1 ulp from the division)
+    const R inv_da = (R)1.0 / ((R)1.0 + (R)2.0 * dtrk * idy2), inv_db = (R)1.0 / ((R)1.0 + (R)2.0 * dtrk * idx2);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int j = g.j0 + blockIdx.y * blockDim.y + threadIdx.y;
     double r = 0.0;
@@ -136,7 +142,7 @@ k_a_sweep(Geo g, R dt, R kappa2, R rho, R H, const uint8_t *__restrict__ nf,
             R lo = 0, hi = 0;
             if (j > 0) lo = idy2 * a[n - P] - idxy * b[n - P] + idxy * b[n - P + 1];
             if (j + 1 < g.Ny) hi = idy2 * a[n + P] + idxy * b[n] - idxy * b[n + 1];
-            R nx = (q + dt_rho * (jl + rh) + dtrk * dd * (lo + hi)) / ((R)1.0 + (R)2.0 * dtrk * idy2);
+            R nx = (q + dt_rho * (jl + rh) + dtrk * dd * (lo + hi)) * inv_da;
             R old = a[n];
             oa[n] = nx;
             r = fabs((double)(nx - old));
@@ -158,7 +164,7 @@ k_a_sweep(Geo g, R dt, R kappa2, R rho, R H, const uint8_t *__restrict__ nf,
             R lo = 0, hi = 0;
             if (i > 0) lo = idx2 * b[n - 1] - idxy * a[n - 1] + idxy * a[n - 1 + P];
             if (i + 1 < g.Nx) hi = idx2 * b[n + 1] + idxy * a[n] - idxy * a[n + P];
-            R nx = (q + dt_rho * (jl + rh) + dtrk * dd * (lo + hi)) / ((R)1.0 + (R)2.0 * dtrk * idx2);
+            R nx = (q + dt_rho * (jl + rh) + dtrk * dd * (lo + hi)) * inv_db;
             R old = b[n];
             ob[n] = nx;
             r = fmax(r, fabs((double)(nx - old)));
@@ -215,6 +221,24 @@ static int read_resid(svl_ctx *c, int first, int count) {
                               cudaMemcpyDeviceToHost, c->stream));
     SVL_CHECK(cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+// How many sweeps to launch before the next read-back.
+// First batch: the previous solve's count, lowered by its last drop (counts fall monotonically
+// while the system relaxes); 8 when there is no history.
+static int first_batch(int last, int before) {
+    if (last <= 0) return 8;
+    int drop = before > last ? before - last : 0;
+    int n = last - drop;
+    return n < 1 ? 1 : n;
+}
+// Continuation: the Jacobi update norm decays geometrically, r_{s+1} ~ rho r_s, so the number
+// of sweeps still missing is about log(eps/r)/log(rho); launch that many (bounded), then look again.
+static int more_sweeps(double r_prev, double r_last, double eps) {
+    if (!(r_last > 0.0) || !(r_prev > r_last)) return 2;
+    double n = ceil(log(eps / r_last) / log(r_last / r_prev));
+    if (!(n >= 1.0)) return 1;
+    return n > 32.0 ? 32 : (int)n;
 }
 
 static int check_kinds(const svl_buf *psi, const svl_buf *ab, const svl_buf *epsf) {
@@ -284,17 +308,21 @@ struct PsiIter {
 static int psi_launch_range(svl_ctx *c, const PsiSolveArgs &A, PsiIter &it, int s0, int s1, bool tail_single) {
     int s = s0;
     while (s < s1) {
-        int K = 1;
-        if (c->opt_psi_kernel == 1) {
-            K = c->opt_psi_k;
+        int K = 0;                                   // 0: plain per-node kernel (one sweep)
+        if (c->opt_psi_kernel >= 1) {
             int left = s1 - s;
             if (tail_single && left > 1) left -= 1;
-            if (K > left) K = left;
+            int want = c->opt_psi_k < left ? c->opt_psi_k : left;
+            if (c->opt_tma || c->opt_psi_kernel == 2) K = svl_psi_stream_fit_k(want);
+            else K = want >= 4 ? 4 : 0;              // plain-load staging is built for K = 4 only
         }
         svl_buf *out = it.S[it.toggle];
-        if (c->opt_psi_kernel == 1) {
+        if (K > 0 && c->opt_psi_kernel == 2) {
+            SVL_TRY(svl_launch_psi_tile(c, K, A.dt, A.eps, A.epsf, A.ab, it.B0, it.cur, out, A.lang_c, A.rand_t, c->d_resid + s));
+        } else if (K > 0) {
             SVL_TRY(svl_launch_psi_stream(c, K, A.dt, A.eps, A.epsf, A.ab, it.B0, it.cur, out, A.lang_c, A.rand_t, c->d_resid + s));
         } else {
+            K = 1;
             SVL_TRY(svl_launch_psi_sweep(c, A.dt, A.eps, A.epsf, A.ab, it.B0, it.cur, out, A.lang_c, A.rand_t, c->d_resid + s));
         }
         it.prev = it.cur; it.cur = out; it.toggle ^= 1; it.lastK = K;
@@ -315,12 +343,12 @@ extern "C" int svl_td_psi_solve(svl_ctx *c, double dt, double eps, const svl_buf
     PsiSolveArgs A = {dt, eps, epsf, ab, lang_c, rand_t};
     SVL_CHECK(cudaMemsetAsync(c->d_resid, 0, SVL_MAX_SWEEPS * sizeof(unsigned long long), c->stream));
     int done = 0, nstop = -1;
-    int pred = c->pred_psi;
-    if (pred > SVL_MAX_SWEEPS) pred = SVL_MAX_SWEEPS;
     while (nstop < 0) {
-        int upto = done == 0 && pred > 0 ? pred : done + 1;
+        int upto;
+        if (done == 0) upto = first_batch(c->pred_psi, c->pred_psi2);
+        else upto = done + more_sweeps(done >= 2 ? slot_value(c->h_resid[done - 2]) : 0.0, slot_value(c->h_resid[done - 1]), stop_eps);
         if (upto > SVL_MAX_SWEEPS) upto = SVL_MAX_SWEEPS;
-        SVL_TRY(psi_launch_range(c, A, it, done, upto, true));
+        SVL_TRY(psi_launch_range(c, A, it, done, upto, c->opt_psi_kernel == 0));
         SVL_TRY(read_resid(c, done, upto - done));
         for (int s = done; s < upto; s++)
             if (stop_rule(c, slot_value(c->h_resid[s]), stop_eps)) { nstop = s + 1; break; }
@@ -329,15 +357,25 @@ extern "C" int svl_td_psi_solve(svl_ctx *c, double dt, double eps, const svl_buf
     }
     // `done` sweeps were executed; the reference stops after nstop <= done sweeps
     svl_buf *res = it.cur;
-    if (nstop == done - 1 && it.lastK == 1 && it.prev != it.B0) {
-        res = it.prev;                       // iterate before the last single sweep is still intact
-    } else if (nstop < done) {
-        c->stat_replays += 1;
-        it.reset();
-        SVL_TRY(psi_launch_range(c, A, it, 0, nstop, false));
-        res = it.cur;
+    if (nstop < done) {
+        int first_of_last = done - it.lastK;            // first sweep index of the last launch
+        if (nstop == first_of_last && it.prev != it.B0) {
+            res = it.prev;                               // the input of the last launch is the answer
+        } else if (nstop > first_of_last) {
+            // overshoot inside the last launch: redo only that launch, shorter (its input is intact)
+            c->stat_replays += 1;
+            it.cur = it.prev; it.toggle ^= 1;
+            SVL_TRY(psi_launch_range(c, A, it, first_of_last, nstop, false));
+            res = it.cur;
+        } else {
+            c->stat_replays += 1;
+            it.reset();
+            SVL_TRY(psi_launch_range(c, A, it, 0, nstop, false));
+            res = it.cur;
+        }
     }
     SVL_TRY(svl_swap(c, psi, res));
+    c->pred_psi2 = c->pred_psi;
     c->pred_psi = nstop;
     c->stat_psi_sweeps += nstop;
     if (sweeps_out) *sweeps_out = nstop;
@@ -374,10 +412,10 @@ extern "C" int svl_td_a_solve(svl_ctx *c, double dt, double kappa2, double rho, 
     ASolveArgs A = {dt, kappa2, rho, H, psi, lang_c, rand_t};
     SVL_CHECK(cudaMemsetAsync(c->d_resid, 0, SVL_MAX_SWEEPS * sizeof(unsigned long long), c->stream));
     int done = 0, nstop = -1;
-    int pred = c->pred_A;
-    if (pred > SVL_MAX_SWEEPS) pred = SVL_MAX_SWEEPS;
     while (nstop < 0) {
-        int upto = done == 0 && pred > 0 ? pred : done + 1;
+        int upto;
+        if (done == 0) upto = first_batch(c->pred_A, c->pred_A2);
+        else upto = done + more_sweeps(done >= 2 ? slot_value(c->h_resid[done - 2]) : 0.0, slot_value(c->h_resid[done - 1]), stop_eps);
         if (upto > SVL_MAX_SWEEPS) upto = SVL_MAX_SWEEPS;
         SVL_TRY(a_launch_range(c, A, ab, S1, S2, done, upto));
         SVL_TRY(read_resid(c, done, upto - done));
@@ -392,6 +430,7 @@ extern "C" int svl_td_a_solve(svl_ctx *c, double dt, double kappa2, double rho, 
     }
     svl_buf *res = ((nstop - 1) & 1) ? S2 : S1;
     SVL_TRY(svl_swap(c, ab, res));
+    c->pred_A2 = c->pred_A;
     c->pred_A = nstop;
     c->stat_A_sweeps += nstop;
     if (sweeps_out) *sweeps_out = nstop;

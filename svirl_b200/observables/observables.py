@@ -35,9 +35,9 @@ class Observables(object):
     @property
     def magnetic_field(self):
         """Induced magnetic field on cells."""
-        self.vars._vp.sync()
+        self.vars._vp.push()
         if self.params._vpei is not None:
-            self.params._vpei.sync()
+            self.params._vpei.push()
         _lib.call("svl_magnetic_field", self.par.ctx, _h(self.params.external_irregular_vector_potential_h()),
                   _h(self.vars.vector_potential_h()), self.vars._tmp_cell_var_h().handle)
         self.vars._tmp_cell_var.need_dtoh_sync()
@@ -46,10 +46,10 @@ class Observables(object):
     @property
     def supercurrent_density(self):
         """Superconducting current density on (horizontal, vertical) edges."""
-        self.vars._psi.sync()
-        self.vars._vp.sync()
+        self.vars._psi.push()
+        self.vars._vp.push()
         if self.params._vpei is not None:
-            self.params._vpei.sync()
+            self.params._vpei.push()
         _lib.call("svl_supercurrent_density", self.par.ctx, self.vars.order_parameter_h().handle,
                   _h(self.params.external_irregular_vector_potential_h()), _h(self.vars.vector_potential_h()),
                   self.vars._tmp_edge_var_h().handle)
@@ -62,9 +62,9 @@ class Observables(object):
         """Total current density on edges; equals the supercurrent when kappa is infinite."""
         if not self.params.solveA:
             return self.supercurrent_density
-        self.vars._vp.sync()
+        self.vars._vp.push()
         if self.params._vpei is not None:
-            self.params._vpei.sync()
+            self.params._vpei.push()
         _lib.call("svl_current_density", self.par.ctx, float(self.params.gl_parameter_squared_h()),
                   float(self.params.homogeneous_external_field),
                   _h(self.params.external_irregular_vector_potential_h()), _h(self.vars.vector_potential_h()),
@@ -82,8 +82,8 @@ class Observables(object):
     @property
     def free_energy(self):
         """Total GL free energy."""
-        self.vars._psi.sync()
-        self.vars._vp.sync()
+        self.vars._psi.push()
+        self.vars._vp.push()
         eps, epsf = self._eps_args()
         E = C.c_double()
         _lib.call("svl_free_energy", self.par.ctx, float(self.params.gl_parameter_squared_h()), eps, epsf,

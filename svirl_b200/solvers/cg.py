@@ -45,9 +45,9 @@ class CG(object):
     # ---- argument helpers
     def _state(self):
         p = self.params
-        self.vars._psi.sync()
+        self.vars._psi.push()
         if self.vars._vp is not None:
-            self.vars._vp.sync()
+            self.vars._vp.push()
         eps = float(np.asarray(p.linear_coefficient_scalar_h()).reshape(-1)[0])
         return dict(k2=float(p.gl_parameter_squared_h()), eps=eps, epsf=_h(p.linear_coefficient_h()),
                     H=float(p.homogeneous_external_field), psi=self.vars.order_parameter_h().handle,

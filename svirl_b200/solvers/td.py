@@ -82,8 +82,8 @@ class TD(object):
 
     def _run(self, Nt, dt, do_psi=True, do_A=True):
         p = self.params
-        self.vars._psi.sync()
-        self.vars._vp.sync()
+        self.vars._psi.push()
+        self.vars._vp.push()
         eps, epsf = self._eps_args()
         psi, ab = self.vars.order_parameter_h(), self.vars.vector_potential_h()
         rt = C.c_uint32(int(self._random_t))

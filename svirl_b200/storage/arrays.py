@@ -273,6 +273,14 @@ class GArray(object):
             self._gdata.set(self._data)
         self.synced()
 
+    def push(self):
+        """Make the device copy current WITHOUT pulling device data back: host-to-device copy
+        only if the host side was modified (used at solver entry; the reference's solvers do not
+        read the fields back between calls either)."""
+        if self._hd() and self.__sync_status is not None and self.__sync_status < 0:
+            self._gdata.set(self._data)
+            self.synced()
+
     def need_dtoh_sync(self):
         if self._hd():
             self.__sync_status = 1

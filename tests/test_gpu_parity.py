@@ -31,7 +31,8 @@ def relerr(x, ref):
 # psi-sweep kernel variants: plain per-node kernel, streaming kernel (TMA staging) at several
 # temporal-blocking depths, and the streaming kernel with plain-load staging
 KERNELS = [("plain", 0, 1, 1), ("stream_k4_tma", 1, 4, 1), ("stream_k1_tma", 1, 1, 1), ("stream_k3_tma", 1, 3, 1),
-           ("stream_k6_tma", 1, 6, 1), ("stream_k4_ldg", 1, 4, 0)]
+           ("stream_k6_tma", 1, 6, 1), ("stream_k4_ldg", 1, 4, 0),
+           ("tile_k4", 2, 4, 1), ("tile_k1", 2, 1, 1), ("tile_k3", 2, 3, 1), ("tile_k8", 2, 8, 1)]
 
 
 def set_kernel(gl, kernel):
@@ -178,7 +179,7 @@ def test_cg_full_first_iterations(name):
     assert np.all(np.diff(E) < 0)          # energy decreases monotonically
 
 
-@pytest.mark.parametrize("kernel", [KERNELS[0], KERNELS[1]], ids=["plain", "stream_k4_tma"])
+@pytest.mark.parametrize("kernel", [KERNELS[0], KERNELS[1], KERNELS[6]], ids=["plain", "stream_k4_tma", "tile_k4"])
 def test_cfg1_readme_1000_steps(kernel):
     """BASELINE configs[0]: 129^2, kappa 5, sigma 200, H 0.1, fp64, td(0.1, 1000): psi, a, b within
     1e-10, identical sweep counts, identical vortex count and positions."""
@@ -263,7 +264,7 @@ def test_stream_kernel_equals_plain_kernel_large_grid(dtype):
     mt = rs.rand(Nx - 1, Ny - 1) > 0.15
     eps = (0.7 + 0.3 * rs.rand(Nx, Ny)).astype(dtype)
     out = []
-    for kernel in (KERNELS[0], KERNELS[1], KERNELS[5], KERNELS[3]):
+    for kernel in (KERNELS[0], KERNELS[1], KERNELS[5], KERNELS[3], KERNELS[6], KERNELS[9]):
         gl = GLSolver(Nx=Nx, Ny=Ny, dx=0.5, dy=0.5, dtype=dtype, homogeneous_external_field=0.1, random_seed=5,
                       material_tiling=mt, linear_coefficient=eps)
         set_kernel(gl, kernel)
