@@ -15,7 +15,10 @@ measured HBM copy peak; `cpu_baseline` = the reference's own kernel source compi
 cores (oracle/_ref, kind "reference") or the NumPy port, on a bounded sample.
 
 --impl reference times that CPU arm alone (the reference has no CPU path and pyCUDA cannot be
-installed offline).  With --gpus N > 1 (launched under torchrun) the grid is ...
+installed offline).  With --gpus N > 1 (launched under torchrun, one rank per GPU)
+the grid grows to Nx x (Ny*N) and is decomposed into N row slabs (weak scaling: every GPU keeps the
+N=1 workload); halo rows move by direct peer stores over NVLink and the only collective is the MAX
+of the per-sweep residuals.
 """
 import argparse
 import ctypes as C
@@ -60,11 +63,11 @@ def hole_tiling(Nx, Ny, dx=0.5, dy=0.5):
     return ~((fx[:, None] + fy[None, :]) < 4.0)
 
 
-def make_solver(wl, device_id=0):
+def make_solver(wl, device_id=0, slab=None):
     from svirl_b200 import GLSolver
     kw = dict(Nx=wl["Nx"], Ny=wl["Ny"], dx=0.5, dy=0.5, dtype=wl["dtype"], gl_parameter=wl["kappa"],
               normal_conductivity=wl["sigma"], homogeneous_external_field=wl["H"], random_seed=1234,
-              device_id=device_id)
+              device_id=device_id, slab=slab)
     if wl["tiling"]:
         kw["material_tiling"] = hole_tiling(wl["Nx"], wl["Ny"])
     if wl["eps_field"]:
@@ -210,6 +213,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     wl = workload(args.workload)
+    if world > 1 and args.impl == "ours":
+        wl = dict(wl, Ny=wl["Ny"] * world, name=wl["name"] + " x%d row slabs (Ny=%d)" % (world, wl["Ny"] * world))
     N = wl["Nx"] * wl["Ny"]
     cfgd = {"workload": wl["name"], "Nx": wl["Nx"], "Ny": wl["Ny"], "dt": 0.1, "seed": 1234,
             "l2": "working set (3 psi planes + a,b + flags) exceeds the 126 MB L2" if N >= 2048 * 2048 else
@@ -237,7 +242,7 @@ def main():
     torch.cuda.set_device(local)
 
     from svirl_b200 import _lib
-    gl = make_solver(wl, device_id=local)
+    gl = make_solver(wl, device_id=local, slab="auto" if world > 1 else None)
     par = gl.par
     if args.psi_kernel is not None:
         par.set_option("psi_kernel", args.psi_kernel)
@@ -274,22 +279,26 @@ def main():
         t = torch.tensor([t_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_ms = float(t.item())
-    value = world * N * args.steps / (t_ms * 1e-3)
+    value = N * args.steps / (t_ms * 1e-3)          # N = nodes of the whole (all-rank) grid
 
     # ---- end to end through the C ABI with HOST buffers: psi up, one step, psi down, every step
     cdt = np.complex64 if wl["dtype"] is np.float32 else np.complex128
-    pin_in = torch.empty(N * 2, dtype=torch.float32 if wl["dtype"] is np.float32 else torch.float64).pin_memory()
+    j0, j1 = gl.cfg.slab if gl.cfg.slab is not None else (0, wl["Ny"])
+    nloc = wl["Nx"] * (j1 - j0)                        # this rank's nodes
+    pin_in = torch.empty(nloc * 2, dtype=torch.float32 if wl["dtype"] is np.float32 else torch.float64).pin_memory()
     pin_out = torch.empty_like(pin_in).pin_memory()
     h_in, h_out = pin_in.numpy().view(cdt), pin_out.numpy().view(cdt)
-    h_in[:] = gl.vars._psi.get_d_obj().get()
     psi_h = gl.vars.order_parameter_h().handle
+    _lib.call("svl_d2h_rows", par.ctx, h_in.ctypes.data_as(C.c_void_p), psi_h, 0, int(j0), int(j1))
     e2e_steps = max(3, min(args.steps, 20))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        _lib.call("svl_h2d", par.ctx, psi_h, h_in.ctypes.data_as(C.c_void_p))
+        _lib.call("svl_h2d_rows", par.ctx, psi_h, 0, int(j0), int(j1), h_in.ctypes.data_as(C.c_void_p))
+        if gl.slab_comm is not None:
+            _lib.call("svl_slab_exchange", par.ctx, psi_h)
         gl.solve.td(Nt=1, **td_kw)
-        _lib.call("svl_d2h", par.ctx, h_out.ctypes.data_as(C.c_void_p), psi_h)
+        _lib.call("svl_d2h_rows", par.ctx, h_out.ctypes.data_as(C.c_void_p), psi_h, 0, int(j0), int(j1))
         h_in, h_out = h_out, h_in
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -297,7 +306,7 @@ def main():
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_val = world * N * e2e_steps / e2e_s
+    e2e_val = N * e2e_steps / e2e_s
 
     if rank != 0:
         if world > 1:
@@ -313,7 +322,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     bpsi, bA = bytes_per_node_sweep(wl)
-    alg_bytes = (sw_psi * bpsi + sw_A * bA) * N
+    alg_bytes = (sw_psi * bpsi + sw_A * bA) * (N // world)      # per GPU: the roofline is a per-device quantity
     achieved = alg_bytes / (t_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650",
@@ -334,7 +343,8 @@ def main():
             "dtype": "f32" if wl["dtype"] is np.float32 else "f64", "data": "synthetic", "config": cfgd,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(N * np.dtype(cdt).itemsize),
-                    "d2h_bytes_per_step": int(N * np.dtype(cdt).itemsize), "steps": e2e_steps},
+                    "d2h_bytes_per_step": int(N * np.dtype(cdt).itemsize), "steps": e2e_steps,
+                    "api": "svl_h2d_rows + svl_td_run(1 step) + svl_d2h_rows on pinned host buffers"},
             "gpu_launches": int(launches), "replays": par.stat("replays"),
             "psi_kernel": int(args.psi_kernel) if args.psi_kernel is not None else None}
     print(json.dumps(line))

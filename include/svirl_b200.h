@@ -162,6 +162,19 @@ int svl_vortex_candidates(svl_ctx *ctx, double H, const svl_buf *psi, const svl_
 int svl_sum(svl_ctx *ctx, const svl_buf *in, size_t n, double *out);
 int svl_sum_v(svl_ctx *ctx, const svl_buf *in, size_t nv, int ne, double *out /* [ne] */);
 
+/* ---- multi-GPU row slabs (new) -------------------------------------
+ * One process per GPU; the context owns rows [j0, j1) (svl_create).  svl_slab_export writes
+ * 144 bytes (the CUDA IPC handle of one arena that now holds the psi x3, a x3, b x3 planes and
+ * the flag words, plus their 10 byte offsets) for the neighbours; svl_slab_connect opens the neighbours' handles (NULL at the ends of the chain).
+ * From then on every psi / A launch pushes its boundary rows into the neighbours' halo rows by
+ * direct peer stores and waits for theirs.  The MAX of the per-sweep residual slots over all
+ * ranks goes through reduce_max_u64 (in place on n 64-bit values; exact, so the TD trajectory
+ * does not depend on the slab count). */
+int svl_slab_export(svl_ctx *ctx, svl_buf *psi, svl_buf *ab, void *handles_out);
+int svl_slab_connect(svl_ctx *ctx, const void *lo_handles, int lo_j0, const void *hi_handles, int hi_j0);
+int svl_slab_exchange(svl_ctx *ctx, svl_buf *buf);
+int svl_set_reduce_callback(svl_ctx *ctx, void (*reduce_max_u64)(unsigned long long *vals, int n));
+
 #ifdef __cplusplus
 }
 #endif

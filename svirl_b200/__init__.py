@@ -100,7 +100,14 @@ class GLSolver(object):
         cfg.stop_criterion_order_parameter = cfg.dtype(stop_criterion_order_parameter)
         cfg.stop_criterion_vector_potential = cfg.dtype(stop_criterion_vector_potential)
         cfg.convergence_rtol = convergence_rtol
-        cfg.slab = slab
+        # slab = None (whole grid on this GPU), (j0, j1), or 'auto' (rows split over the ranks of the
+        # default torch.distributed group; neighbours are connected at the end of construction)
+        self._auto_slab = isinstance(slab, str) and slab == 'auto'
+        if self._auto_slab:
+            import torch.distributed as dist
+            from svirl_b200.parallel.slab import partition_rows
+            slab = partition_rows(int(cfg.Ny), dist.get_world_size())[dist.get_rank()]
+        cfg.slab = tuple(int(x) for x in slab) if slab is not None else None
         self.cfg = cfg
 
         # same construction order as the reference (svirl/__init__.py:158-175)
@@ -112,6 +119,10 @@ class GLSolver(object):
         self.observables = GLObs.Observables(self.par, self.mesh, self.vars, self.params)
         self.solve = GLSolvers.Solvers(self.par, self.mesh, self.vars, self.params, self.observables)
         self.vortex_detector = GLObs.VortexDetector(self.vars, self.params, self.solve)
+        self.slab_comm = None
+        if self._auto_slab:
+            from svirl_b200.parallel.slab import SlabComm
+            self.slab_comm = SlabComm(self)
 
     # ---- helpers used by the reference's tests
     def flatten_a_array(self, a):

@@ -55,6 +55,10 @@ SIGNATURES = {
     "svl_current_density": ([_p, _d, _d, _p, _p, _p], _i),
     "svl_supercurrent_density": ([_p, _p, _p, _p, _p], _i),
     "svl_vortex_candidates": ([_p, _d, _p, _p, C.POINTER(C.c_int64), _pd, _sz, C.POINTER(_sz)], _i),
+    "svl_slab_export": ([_p, _p, _p, _p], _i),
+    "svl_slab_connect": ([_p, _p, _i, _p, _i], _i),
+    "svl_slab_exchange": ([_p, _p], _i),
+    "svl_set_reduce_callback": ([_p, _p], _i),
     "svl_sum": ([_p, _p, _sz, _pd], _i),
     "svl_sum_v": ([_p, _p, _sz, _i, _pd], _i),
 }

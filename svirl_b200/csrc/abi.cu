@@ -102,6 +102,7 @@ extern "C" int svl_destroy(svl_ctx *c) {
         if (c->psi_s[k]) svl_free(c, c->psi_s[k]);
         if (c->ab_s[k]) svl_free(c, c->ab_s[k]);
     }
+    cudaFree(c->arena);
     cudaFree(c->nf); cudaFree(c->d_result); cudaFreeHost(c->h_result);
     cudaFree(c->d_resid); cudaFreeHost(c->h_resid); cudaFree(c->d_counter);
     cudaFree(c->partials); cudaFree(c->d_cand); cudaFree(c->d_candv); cudaFree(c->d_ncand);
@@ -221,8 +222,7 @@ extern "C" int svl_alloc(svl_ctx *c, int kind, size_t n, int elem_size, svl_buf 
 extern "C" int svl_free(svl_ctx *c, svl_buf *b) {
     if (!b) return 0;
     if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
-    cudaFree(b->p[0]);
-    cudaFree(b->p[1]);
+    if (!b->borrowed) { cudaFree(b->p[0]); cudaFree(b->p[1]); }
     delete b;
     return 0;
 }

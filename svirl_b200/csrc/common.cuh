@@ -67,6 +67,7 @@ struct svl_buf {
     size_t n;           // elements in the flat (reference) layout
     void *p[2];         // plane(s): [0] nodes/cells/a/flat, [1] b
     size_t bytes[2];
+    int borrowed;       // planes live in the slab arena (slab.cu): svl_free must not cudaFree them
 };
 
 struct svl_ctx {
@@ -96,6 +97,19 @@ struct svl_ctx {
     int pred_psi2, pred_A2;        // ... and of the one before (trend)
     double stat_launches, stat_replays, stat_psi_sweeps, stat_A_sweeps;
     cudaEvent_t ev[8];
+    // ---- slab decomposition (multi-GPU): see slab.cu
+    int slab_on;                   // 1 once svl_slab_connect succeeded
+    int has_lo, has_hi;            // neighbours below (smaller j) / above
+    int nb_rb[2];                  // rb of the lower / upper neighbour
+    void *peer[2][9];              // neighbour plane pointers by physical id: psi x3, a x3, b x3
+    void *own_phys[9];             // this rank's planes by physical id
+    void *arena;                   // one allocation holding the 9 exchanged planes + flags (one IPC handle)
+    unsigned long long *flags;     // [2] written by the neighbours (epoch of their last push into us)
+    unsigned long long *peer_flags[2];   // neighbour's flags array (we write slot [1] of lower, [0] of upper)
+    unsigned long long epoch_psi, epoch_A;   // pushes issued so far
+    unsigned long long waited;               // epoch the last wait kernel covered
+    // residual / sum reduction across ranks (host callback; torch.distributed behind it)
+    void (*reduce_max_u64)(unsigned long long *vals, int n);
 };
 
 static inline int svl_nblocks(size_t n, int b) { return (int)((n + b - 1) / b); }
@@ -110,6 +124,10 @@ int svl_launch_a_sweep(svl_ctx *c, double dt, double kappa2, double rho, double 
 // reduce.cu
 int svl_ensure_partials(svl_ctx *c, size_t n);
 int svl_finish_sum(svl_ctx *c, int nblocks, int nv, double scale, double *out_host);  // partials[nblocks*nv] -> host
+// slab.cu
+int svl_slab_push_psi(svl_ctx *c, const svl_buf *buf);       // boundary rows of a psi buffer -> neighbours' halos
+int svl_slab_push_ab(svl_ctx *c, const svl_buf *buf);
+int svl_slab_wait(svl_ctx *c);                               // wait until all pushes so far have arrived
 // abi.cu
 int svl_scratch_node(svl_ctx *c, int k, svl_buf **out);
 int svl_scratch_edge(svl_ctx *c, int k, svl_buf **out);

@@ -220,6 +220,8 @@ static int read_resid(svl_ctx *c, int first, int count) {
     SVL_CHECK(cudaMemcpyAsync(c->h_resid + first, c->d_resid + first, (size_t)count * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, c->stream));
     SVL_CHECK(cudaStreamSynchronize(c->stream));
+    // slabs: MAX over ranks (bit patterns of non-negative doubles order like integers; exact)
+    if (c->reduce_max_u64) c->reduce_max_u64(c->h_resid + first, count);
     return 0;
 }
 
@@ -317,6 +319,7 @@ static int psi_launch_range(svl_ctx *c, const PsiSolveArgs &A, PsiIter &it, int 
             else K = want >= 4 ? 4 : 0;              // plain-load staging is built for K = 4 only
         }
         svl_buf *out = it.S[it.toggle];
+        SVL_TRY(svl_slab_wait(c));                   // neighbours' halo rows of the input have arrived
         if (K > 0 && c->opt_psi_kernel == 2) {
             SVL_TRY(svl_launch_psi_tile(c, K, A.dt, A.eps, A.epsf, A.ab, it.B0, it.cur, out, A.lang_c, A.rand_t, c->d_resid + s));
         } else if (K > 0) {
@@ -325,6 +328,7 @@ static int psi_launch_range(svl_ctx *c, const PsiSolveArgs &A, PsiIter &it, int 
             K = 1;
             SVL_TRY(svl_launch_psi_sweep(c, A.dt, A.eps, A.epsf, A.ab, it.B0, it.cur, out, A.lang_c, A.rand_t, c->d_resid + s));
         }
+        SVL_TRY(svl_slab_push_psi(c, out));          // my boundary rows -> neighbours' halos (peer stores)
         it.prev = it.cur; it.cur = out; it.toggle ^= 1; it.lastK = K;
         s += K;
     }
@@ -374,6 +378,7 @@ extern "C" int svl_td_psi_solve(svl_ctx *c, double dt, double eps, const svl_buf
             res = it.cur;
         }
     }
+    SVL_TRY(svl_slab_wait(c));                       // halos of the result are complete before anyone reads them
     SVL_TRY(svl_swap(c, psi, res));
     c->pred_psi2 = c->pred_psi;
     c->pred_psi = nstop;
@@ -395,8 +400,10 @@ static int a_launch_range(svl_ctx *c, const ASolveArgs &A, svl_buf *B0, svl_buf 
         const svl_buf *in = s == 0 ? B0 : ((s & 1) ? S1 : S2);
         svl_buf *out = (s & 1) ? S2 : S1;
         const svl_buf *ph = s <= 1 ? B0 : S2;
+        SVL_TRY(svl_slab_wait(c));
         SVL_TRY(svl_launch_a_sweep(c, A.dt, A.kappa2, A.rho, A.H, A.psi, ph, B0, in, out, A.lang_c, A.rand_t, noise,
                                    c->d_resid + s));
+        SVL_TRY(svl_slab_push_ab(c, out));
     }
     return 0;
 }
@@ -429,6 +436,7 @@ extern "C" int svl_td_a_solve(svl_ctx *c, double dt, double kappa2, double rho, 
         SVL_TRY(a_launch_range(c, A, ab, S1, S2, 0, nstop));
     }
     svl_buf *res = ((nstop - 1) & 1) ? S2 : S1;
+    SVL_TRY(svl_slab_wait(c));
     SVL_TRY(svl_swap(c, ab, res));
     c->pred_A2 = c->pred_A;
     c->pred_A = nstop;

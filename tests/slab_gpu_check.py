@@ -1,0 +1,61 @@
+"""Multi-GPU check (run under torchrun on a box with >= 2 GPUs; see tests/test_gpu_slab.py):
+TDGL on row slabs must reproduce the single-GPU trajectory BITWISE (MAX is exact), with the
+same sweep counts, for psi-only and finite-kappa runs."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+
+
+def run(kw, Nt, slab):
+    from svirl_b200 import GLSolver
+    gl = GLSolver(slab=slab, **kw)
+    gl.solve.td(dt=0.1, Nt=Nt)
+    td = gl.solve._td
+    psi = gl.vars._psi.get_d_obj().get()
+    ab = gl.vars._vp.get_d_obj().get()
+    out = (gl.unflatten_array(psi), ab, td.sweeps_order_parameter, td.sweeps_vector_potential, gl.cfg.slab)
+    gl.par.close()
+    return out
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    Nx, Ny = 300, 401
+    rs = np.random.RandomState(3)
+    mt = rs.rand(Nx - 1, Ny - 1) > 0.1
+    ok = True
+    for name, kw, Nt in (
+            ("kinf_f32", dict(dtype=np.float32, material_tiling=mt), 12),
+            ("k2_f64", dict(dtype=np.float64, gl_parameter=2.0, normal_conductivity=10.0, material_tiling=mt), 8)):
+        kw = dict(Nx=Nx, Ny=Ny, dx=0.5, dy=0.5, homogeneous_external_field=0.1, random_seed=5, device_id=local, **kw)
+        psi_s, ab_s, ns, na, slab = run(kw, Nt, "auto")
+        psi_1, ab_1, ns1, na1, _ = run(kw, Nt, None)            # every rank also runs the whole grid alone
+        j0, j1 = slab
+        same_psi = np.array_equal(psi_s[:, j0:j1], psi_1[:, j0:j1])
+        Na = (Nx - 1) * Ny
+        a_s, a_1 = ab_s[:Na].reshape(Ny, Nx - 1), ab_1[:Na].reshape(Ny, Nx - 1)
+        b_s, b_1 = ab_s[Na:].reshape(Ny - 1, Nx), ab_1[Na:].reshape(Ny - 1, Nx)
+        same_a = np.array_equal(a_s[j0:j1], a_1[j0:j1]) and np.array_equal(b_s[j0:min(j1, Ny - 1)], b_1[j0:min(j1, Ny - 1)])
+        good = same_psi and same_a and (ns, na) == (ns1, na1)
+        print("rank %d %s: rows [%d,%d) psi bitwise %s, A bitwise %s, sweeps %d/%d vs %d/%d -> %s"
+              % (rank, name, j0, j1, same_psi, same_a, ns, na, ns1, na1, "OK" if good else "MISMATCH"), flush=True)
+        ok = ok and good
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("SLAB CHECK", "PASSED" if int(t.item()) == 1 else "FAILED", flush=True)
+    sys.exit(0 if int(t.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
