@@ -174,6 +174,9 @@ int svl_slab_export(svl_ctx *ctx, svl_buf *psi, svl_buf *ab, void *handles_out);
 int svl_slab_connect(svl_ctx *ctx, const void *lo_handles, int lo_j0, const void *hi_handles, int hi_j0);
 int svl_slab_exchange(svl_ctx *ctx, svl_buf *buf);
 int svl_set_reduce_callback(svl_ctx *ctx, void (*reduce_max_u64)(unsigned long long *vals, int n));
+/* same on device words, with the reduction enqueued on the context's stream (svl_get_stream) */
+int svl_set_reduce_callback_device(svl_ctx *ctx, void (*reduce_max_dev)(unsigned long long *dvals, int n));
+void *svl_get_stream(svl_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -59,6 +59,8 @@ SIGNATURES = {
     "svl_slab_connect": ([_p, _p, _i, _p, _i], _i),
     "svl_slab_exchange": ([_p, _p], _i),
     "svl_set_reduce_callback": ([_p, _p], _i),
+    "svl_set_reduce_callback_device": ([_p, _p], _i),
+    "svl_get_stream": ([_p], _p),
     "svl_sum": ([_p, _p, _sz, _pd], _i),
     "svl_sum_v": ([_p, _p, _sz, _i, _pd], _i),
 }

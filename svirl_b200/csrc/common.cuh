@@ -104,12 +104,15 @@ struct svl_ctx {
     void *peer[2][9];              // neighbour plane pointers by physical id: psi x3, a x3, b x3
     void *own_phys[9];             // this rank's planes by physical id
     void *arena;                   // one allocation holding the 9 exchanged planes + flags (one IPC handle)
-    unsigned long long *flags;     // [2] written by the neighbours (epoch of their last push into us)
+    unsigned long long *flags;     // [2] written by the neighbours
+    unsigned long long *scratch_flag;    // sink for pushes that must not publish
     unsigned long long *peer_flags[2];   // neighbour's flags array (we write slot [1] of lower, [0] of upper)
     unsigned long long epoch_psi, epoch_A;   // pushes issued so far
     unsigned long long waited;               // epoch the last wait kernel covered
     // residual / sum reduction across ranks (host callback; torch.distributed behind it)
-    void (*reduce_max_u64)(unsigned long long *vals, int n);
+    void (*reduce_max_u64)(unsigned long long *vals, int n);      // host values
+    void (*reduce_max_dev)(unsigned long long *dvals, int n);     // device values, enqueued on c->stream
+    unsigned int *push_count;      // [2] completion counters of the push kernel
 };
 
 static inline int svl_nblocks(size_t n, int b) { return (int)((n + b - 1) / b); }
@@ -128,6 +131,8 @@ int svl_finish_sum(svl_ctx *c, int nblocks, int nv, double scale, double *out_ho
 int svl_slab_push_psi(svl_ctx *c, const svl_buf *buf);       // boundary rows of a psi buffer -> neighbours' halos
 int svl_slab_push_ab(svl_ctx *c, const svl_buf *buf);
 int svl_slab_wait(svl_ctx *c);                               // wait until all pushes so far have arrived
+unsigned long long svl_slab_epoch(svl_ctx *c);               // pushes issued so far (what a consumer must wait for)
+void svl_slab_mark_waited(svl_ctx *c);                       // the next kernel waits by itself
 // abi.cu
 int svl_scratch_node(svl_ctx *c, int k, svl_buf **out);
 int svl_scratch_edge(svl_ctx *c, int k, svl_buf **out);

@@ -25,6 +25,10 @@ struct TileArgs {
     int same_rhs;
     void *out;
     unsigned long long *slots;
+    // slabs: halo rows of the input must have arrived (epoch flags written by the neighbours)
+    const unsigned long long *wait_flags;
+    unsigned long long wait_epoch;
+    int has_lo, has_hi;
 };
 
 __device__ __forceinline__ uint32_t t_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -109,6 +113,17 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(t_smem_u32(bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (A.wait_flags) {
+            for (int sdir = 0; sdir < 2; sdir++) {
+                if (!(sdir == 0 ? A.has_lo : A.has_hi)) continue;
+                unsigned long long v = 0;
+                long long t0 = clock64();
+                do {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(A.wait_flags + sdir) : "memory");
+                    if (clock64() - t0 > 20000000000ll) __trap();
+                } while (v < A.wait_epoch);
+            }
+        }
         if (tile < ntiles) issue(tile);
     }
     // zero the pad ring of the exchange / coefficient tiles once (never overwritten afterwards)
@@ -379,6 +394,10 @@ int svl_launch_psi_tile(svl_ctx *c, int K, double dt, double eps, const svl_buf 
     A.noise = lang_c > 1.0e-32 ? 1 : 0;
     A.same_rhs = rhs->p[0] == psi->p[0];
     A.out = out->p[0]; A.slots = resid_slots;
+    if (c->slab_on) {
+        A.wait_flags = c->flags; A.wait_epoch = svl_slab_epoch(c); A.has_lo = c->has_lo; A.has_hi = c->has_hi;
+        svl_slab_mark_waited(c);
+    }
     TileIO io = {psi->p[0], rhs->p[0], ab->p[0], ab->p[1], epsf ? epsf->p[0] : nullptr, c->nf};
     if (c->rsize == 4) {
         if (epsf) return launch_tile_k<float, 64, 8, 4, true>(c, K, A, io);

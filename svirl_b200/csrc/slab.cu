@@ -28,18 +28,34 @@ static int phys_of(const svl_ctx *c, const void *p) {
     return -1;
 }
 
-// copy `depth` rows of `width_bytes` each: src/dst are plane base pointers, rows given as plane rows
-__global__ void __launch_bounds__(256)
-k_push_rows(const unsigned char *src, int src_row, unsigned char *dst, int dst_row, int depth, size_t pitch_bytes) {
-    const uint4 *s = (const uint4 *)(src + (size_t)src_row * pitch_bytes);
-    uint4 *d = (uint4 *)(dst + (size_t)dst_row * pitch_bytes);
-    size_t n = (size_t)depth * pitch_bytes / 16;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) d[i] = s[i];
-}
+// One kernel per push: blockIdx.y = direction (0: to the lower neighbour, 1: to the upper one).
+// Every CTA copies its share of the boundary rows with 16-byte peer stores; the last CTA of a
+// direction to finish publishes the epoch in the neighbour's flag word.
+struct PushDesc {
+    const unsigned char *src[2];
+    unsigned char *dst[2];
+    unsigned long long *flag[2];
+    size_t bytes;
+};
 
-__global__ void k_publish(unsigned long long *flag, unsigned long long epoch) {
+__global__ void __launch_bounds__(256)
+k_push(PushDesc d, unsigned long long epoch, unsigned int *count) {
+    const int dir = blockIdx.y;
+    if (!d.dst[dir]) return;
+    const uint4 *s = (const uint4 *)d.src[dir];
+    uint4 *t = (uint4 *)d.dst[dir];
+    size_t n = d.bytes / 16;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) t[i] = s[i];
     __threadfence_system();
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int done = atomicAdd(&count[dir], 1u);
+        if (done == gridDim.x - 1) {
+            count[dir] = 0;
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(d.flag[dir]), "l"(epoch) : "memory");
+        }
+    }
 }
 
 __global__ void k_wait_flags(const unsigned long long *flags, int has_lo, int has_hi, unsigned long long epoch) {
@@ -54,47 +70,56 @@ __global__ void k_wait_flags(const unsigned long long *flags, int has_lo, int ha
     }
 }
 
-static int push_plane(svl_ctx *c, const void *plane, int esize) {
+// planes[] : 1 (psi) or 2 (a, b) planes of one buffer; they are pushed with ONE epoch
+static int push_planes(svl_ctx *c, const void *const *planes, int nplanes, int esize, unsigned long long epoch) {
     const Geo &g = c->g;
-    int id = phys_of(c, plane);
-    SVL_REQUIRE(id >= 0, "slab push: buffer is not one of the registered planes");
     size_t pitch = (size_t)g.P * esize;
     int rows = g.j1 - g.j0;
     int depth = SVL_HALO < rows ? SVL_HALO : rows;
-    int nb = (int)((depth * pitch / 16 + 255) / 256);
-    if (nb > 296) nb = 296;
-    if (c->has_lo)   // my lowest rows -> lower neighbour's upper halo (same global rows)
-        k_push_rows<<<nb, 256, 0, c->stream>>>((const unsigned char *)plane, g.j0 - g.rb, (unsigned char *)c->peer[0][id],
-                                               g.j0 - c->nb_rb[0], depth, pitch);
-    if (c->has_hi)
-        k_push_rows<<<nb, 256, 0, c->stream>>>((const unsigned char *)plane, g.j1 - depth - g.rb, (unsigned char *)c->peer[1][id],
-                                               g.j1 - depth - c->nb_rb[1], depth, pitch);
-    SVL_CHECK(cudaGetLastError());
-    return 0;
-}
-
-static int publish(svl_ctx *c) {
-    unsigned long long e = c->epoch_psi + c->epoch_A;
-    if (c->has_lo) k_publish<<<1, 1, 0, c->stream>>>(c->peer_flags[0] + 1, e);   // I am the lower neighbour's "hi"
-    if (c->has_hi) k_publish<<<1, 1, 0, c->stream>>>(c->peer_flags[1] + 0, e);
-    SVL_CHECK(cudaGetLastError());
+    for (int q = 0; q < nplanes; q++) {
+        int id = phys_of(c, planes[q]);
+        SVL_REQUIRE(id >= 0, "slab push: buffer is not one of the registered planes");
+        PushDesc d;
+        memset(&d, 0, sizeof(d));
+        d.bytes = (size_t)depth * pitch;
+        if (c->has_lo) {   // my lowest rows -> lower neighbour's upper halo (same global rows)
+            d.src[0] = (const unsigned char *)planes[q] + (size_t)(g.j0 - g.rb) * pitch;
+            d.dst[0] = (unsigned char *)c->peer[0][id] + (size_t)(g.j0 - c->nb_rb[0]) * pitch;
+            d.flag[0] = c->peer_flags[0] + 1;          // I am the lower neighbour's "hi"
+        }
+        if (c->has_hi) {
+            d.src[1] = (const unsigned char *)planes[q] + (size_t)(g.j1 - depth - g.rb) * pitch;
+            d.dst[1] = (unsigned char *)c->peer[1][id] + (size_t)(g.j1 - depth - c->nb_rb[1]) * pitch;
+            d.flag[1] = c->peer_flags[1] + 0;
+        }
+        // only the last plane of a buffer publishes the new epoch (stream order: earlier planes are complete)
+        unsigned long long e = q == nplanes - 1 ? epoch : 0;
+        if (q < nplanes - 1) { d.flag[0] = d.flag[0] ? c->scratch_flag : nullptr; d.flag[1] = d.flag[1] ? c->scratch_flag : nullptr; }
+        int nb = (int)((d.bytes / 16 + 2047) / 2048);
+        if (nb < 1) nb = 1;
+        if (nb > 64) nb = 64;
+        k_push<<<dim3(nb, 2), 256, 0, c->stream>>>(d, e, c->push_count);
+        SVL_CHECK(cudaGetLastError());
+    }
     return 0;
 }
 
 int svl_slab_push_psi(svl_ctx *c, const svl_buf *buf) {
     if (!c->slab_on) return 0;
-    SVL_TRY(push_plane(c, buf->p[0], buf->esize));
     c->epoch_psi += 1;
-    return publish(c);
+    const void *pl[1] = {buf->p[0]};
+    return push_planes(c, pl, 1, buf->esize, c->epoch_psi + c->epoch_A);
 }
 
 int svl_slab_push_ab(svl_ctx *c, const svl_buf *buf) {
     if (!c->slab_on) return 0;
-    SVL_TRY(push_plane(c, buf->p[0], buf->esize));
-    SVL_TRY(push_plane(c, buf->p[1], buf->esize));
     c->epoch_A += 1;
-    return publish(c);
+    const void *pl[2] = {buf->p[0], buf->p[1]};
+    return push_planes(c, pl, 2, buf->esize, c->epoch_psi + c->epoch_A);
 }
+
+unsigned long long svl_slab_epoch(svl_ctx *c) { return c->epoch_psi + c->epoch_A; }
+void svl_slab_mark_waited(svl_ctx *c) { c->waited = c->epoch_psi + c->epoch_A; }
 
 int svl_slab_wait(svl_ctx *c) {
     if (!c->slab_on) return 0;
@@ -137,6 +162,9 @@ extern "C" int svl_slab_export(svl_ctx *c, svl_buf *psi, svl_buf *ab, void *hand
     }
     for (int k = 0; k < 6; k++) bufs[k]->borrowed = 1;
     c->flags = (unsigned long long *)((char *)c->arena + h->off[9]);
+    c->scratch_flag = c->flags + 8;                    // sink for the non-final planes of a push
+    SVL_CHECK(cudaMalloc(&c->push_count, 2 * sizeof(unsigned int)));
+    SVL_CHECK(cudaMemset(c->push_count, 0, 2 * sizeof(unsigned int)));
     SVL_CHECK(cudaIpcGetMemHandle(&h->h, c->arena));
     SVL_CHECK(cudaDeviceSynchronize());
     return 0;
@@ -168,6 +196,16 @@ extern "C" int svl_set_reduce_callback(svl_ctx *c, void (*reduce_max_u64)(unsign
     c->reduce_max_u64 = reduce_max_u64;
     return 0;
 }
+
+// Device-side variant: the callback reduces n device words in place with work enqueued on the
+// context's stream (svl_get_stream), so no extra host synchronisation is needed.
+extern "C" int svl_set_reduce_callback_device(svl_ctx *c, void (*reduce_max_dev)(unsigned long long *, int)) {
+    SVL_REQUIRE(c, "null context");
+    c->reduce_max_dev = reduce_max_dev;
+    return 0;
+}
+
+extern "C" void *svl_get_stream(svl_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
 // Fill the halo rows of a field from the neighbours (used once after the fields were set).
 extern "C" int svl_slab_exchange(svl_ctx *c, svl_buf *buf) {

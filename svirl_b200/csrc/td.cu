@@ -217,11 +217,12 @@ static inline double slot_value(unsigned long long bits) {
 }
 
 static int read_resid(svl_ctx *c, int first, int count) {
+    // slabs: MAX over ranks (bit patterns of non-negative doubles order like integers; exact)
+    if (c->reduce_max_dev) c->reduce_max_dev(c->d_resid + first, count);      // enqueued on c->stream
     SVL_CHECK(cudaMemcpyAsync(c->h_resid + first, c->d_resid + first, (size_t)count * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, c->stream));
     SVL_CHECK(cudaStreamSynchronize(c->stream));
-    // slabs: MAX over ranks (bit patterns of non-negative doubles order like integers; exact)
-    if (c->reduce_max_u64) c->reduce_max_u64(c->h_resid + first, count);
+    if (c->reduce_max_u64 && !c->reduce_max_dev) c->reduce_max_u64(c->h_resid + first, count);
     return 0;
 }
 

@@ -67,6 +67,23 @@ class SlabComm(object):
 
         self._cb = _reduce                                   # keep the callback alive
         _lib.call("svl_set_reduce_callback", par.ctx, C.cast(self._cb, C.c_void_p))
+        if dist.get_backend(group) == "nccl":
+            # NCCL can reduce the device words in place, ordered on the library's own stream
+            import torch
+            stream = torch.cuda.ExternalStream(int(_lib.load().svl_get_stream(par.ctx)))
+
+            class _Dev(object):
+                def __init__(self, ptr, n):
+                    self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+            @C.CFUNCTYPE(None, C.c_void_p, C.c_int)
+            def _reduce_dev(ptr, n):
+                with torch.cuda.stream(stream):
+                    t = torch.as_tensor(_Dev(int(ptr), int(n)), device="cuda")
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+
+            self._cb_dev = _reduce_dev
+            _lib.call("svl_set_reduce_callback_device", par.ctx, C.cast(self._cb_dev, C.c_void_p))
         dist.barrier(group=group)
 
     def exchange(self, garray):
