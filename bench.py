@@ -46,6 +46,15 @@ def workload(name):
     if name == "cfg3":
         return dict(name="cfg3: TDGL kappa=2 8192^2 fp64, disordered eps", Nx=8192, Ny=8192, dtype=np.float64,
                     kappa=2.0, sigma=10.0, H=0.1, tiling=False, eps_field=True)
+    if name == "cfg4":
+        return dict(name="cfg4: CG minimiser 16384^2 fp64 kappa=2 (20 TD steps, then CG iterations)", Nx=16384, Ny=16384,
+                    dtype=np.float64, kappa=2.0, sigma=10.0, H=0.1, tiling=False, eps_field=False, cg=True)
+    if name == "cfg4s":
+        return dict(name="cfg4s: CG minimiser 8192^2 fp64 kappa=2", Nx=8192, Ny=8192, dtype=np.float64, kappa=2.0,
+                    sigma=10.0, H=0.1, tiling=False, eps_field=False, cg=True)
+    if name == "cfg4inf":
+        return dict(name="cfg4inf: CG minimiser 8192^2 fp32 kappa=inf tiled", Nx=8192, Ny=8192, dtype=np.float32,
+                    kappa=np.inf, sigma=1.0, H=0.1, tiling=True, eps_field=False, cg=True)
     if name == "cfg1":
         return dict(name="cfg1: README 129^2 fp64 kappa=5", Nx=129, Ny=129, dtype=np.float64, kappa=5.0, sigma=200.0,
                     H=0.1, tiling=False, eps_field=False)
@@ -195,6 +204,60 @@ def cpu_reference_steps(wl, nsteps, warmup=0):
     return N * nsteps / el, dict(kind="reference", cores=os.cpu_count(), sweeps=sweeps, seconds=el)
 
 
+# ------------------------------------------------------------------------------------ CG mode
+def bench_cg(args, wl, gl, par, N):
+    """Hot path 2: modified nonlinear-CG iterations (metric: CG iterations / s), single GPU.
+    20 TDGL steps leave the random initial state, W warm-up iterations, then K timed ones; the
+    host line search (numpy polyroots / SciPy BFGS, the reference's calls) is inside the timed
+    region because it is part of an iteration."""
+    from svirl_b200 import _lib
+    gl.solve.td(dt=0.1, Nt=20)
+    gl.cfg.convergence_rtol = 0.0
+    gl.solve._init_cg()
+    gl.solve._cg._CG__convergence_rtol = -1.0          # never stop early: time exactly K iterations
+    gl.solve.cg(n_iter=max(args.warmup, 3))
+    par.synchronize()
+    l0 = par.stat("launches")
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0 = time.perf_counter()
+    _lib.call("svl_event_record", par.ctx, 0)
+    gl.solve.cg(n_iter=args.steps)
+    _lib.call("svl_event_record", par.ctx, 1)
+    ms = C.c_double()
+    _lib.call("svl_event_elapsed_ms", par.ctx, 0, 1, C.byref(ms))
+    par.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = par.stat("launches") - l0
+    R = np.dtype(wl["dtype"]).itemsize
+    finite = not np.isinf(wl["kappa"])
+    per_iter = (36 * R + 2) if finite else (22 * R + 2)          # SURVEY 8d: fused lower bounds
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = per_iter * N * args.steps / (ms.value * 1e-3) / 1e9
+    E = gl.solve._cg.cg_energies
+    line = {"metric": "cg_iters_per_s", "value": args.steps / (ms.value * 1e-3), "unit": "iterations/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms.value / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if wl["dtype"] is np.float32 else "f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "Nx": wl["Nx"], "Ny": wl["Ny"], "seed": 1234},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "bytes_per_node_iter": per_iter,
+                         "note": "algorithmic bytes = fused lower bound of SURVEY 8d; includes the host line search time"},
+            "cpu_baseline": None, "clocks": clocks, "gpu_launches": int(launches),
+            "wall_ms_per_iter": 1e3 * wall / args.steps, "energy_first_last": [float(E[0]), float(E[-1])],
+            "e2e": {"value": args.steps / wall, "unit": "iterations/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 8 * (17 if finite else 5) + 8,
+                    "api": "gl.solve.cg(): per iteration the 5/17 coefficients and the energy come back to the host"}}
+    print(json.dumps(line))
+
+
 # ------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -249,6 +312,8 @@ def main():
     if args.psi_k is not None:
         par.set_option("psi_k", args.psi_k)
     td_kw = dict(dt=0.1)
+    if wl.get("cg"):
+        return bench_cg(args, wl, gl, par, N)
 
     def barrier():
         par.synchronize()

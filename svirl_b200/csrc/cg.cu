@@ -338,6 +338,80 @@ __global__ void __launch_bounds__(256) k_beta_sums(const R *__restrict__ gj, con
     block_sum_to_partials<2>(v, partials, blockIdx.x);
 }
 
+// ----------------------------------------------------------------------------- fused CG kernels
+// Both Jacobians of node (i,j) (psi, its a-edge and its b-edge) in one pass, plus the four
+// Polak-Ribiere partial sums  sum g.(g-gp), sum gp.gp  for psi and for A (svirl/cuda/utils.h:13-70).
+template <typename R, bool SOLVEA, bool PREV>
+__global__ void __launch_bounds__(256)
+k_cg_grad(Geo g, R kappa2, R eps, const R *__restrict__ epsf, R H, const uint8_t *__restrict__ nf,
+          const typename V2<R>::type *__restrict__ psi, const R *__restrict__ ae, const R *__restrict__ be,
+          const R *__restrict__ a, const R *__restrict__ b, typename V2<R>::type *__restrict__ gpsi,
+          R *__restrict__ ga, R *__restrict__ gb, const typename V2<R>::type *__restrict__ ppsi,
+          const R *__restrict__ pa, const R *__restrict__ pb, double *partials) {
+    typedef typename V2<R>::type C;
+    const R dx = (R)g.dx, dy = (R)g.dy, idx = (R)g.idx, idy = (R)g.idy;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = g.j0 + blockIdx.y * blockDim.y + threadIdx.y;
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    if (i < g.Nx && j < g.j1) {
+        size_t n = g.at(i, j);
+        unsigned f = nf[n];
+        C gj = node_jac_psi<R, C>(g, n, f, epsf ? epsf[n] : eps, psi, ae, be, a, b);
+        gpsi[n] = gj;
+        if (PREV) {
+            C p = ppsi[n];
+            v[0] = (double)(gj.x * (gj.x - p.x) + gj.y * (gj.y - p.y));
+            v[1] = (double)(p.x * p.x + p.y * p.y);
+        }
+        if (SOLVEA) {
+            C p0 = psi[n];
+            R mp = (f & NF_MP) ? (R)1 : (R)0, pm = (f & NF_PM) ? (R)1 : (R)0, pp = (f & NF_PP) ? (R)1 : (R)0;
+            if (i < g.Nx - 1) {
+                R w = kappa2 * curlcurl_a<R>(g, i, j, n, H, ae, be, a, b);
+                if (f & (NF_PM | NF_PP))
+                    w += -((R)0.5 * (pm + pp)) * idx * js_link<R, C>(p0, dx * edge_sum<R>(ae, a, n), psi[n + 1]);
+                w = (R)2.0 * dx * dy * w;
+                ga[n] = w;
+                if (PREV) { R p = pa[n]; v[2] += (double)(w * (w - p)); v[3] += (double)(p * p); }
+            }
+            if (j < g.Ny - 1) {
+                R w = kappa2 * curlcurl_b<R>(g, i, j, n, H, ae, be, a, b);
+                if (f & (NF_MP | NF_PP))
+                    w += -((R)0.5 * (mp + pp)) * idy * js_link<R, C>(p0, dy * edge_sum<R>(be, b, n), psi[n + g.P]);
+                w = (R)2.0 * dx * dy * w;
+                gb[n] = w;
+                if (PREV) { R p = pb[n]; v[2] += (double)(w * (w - p)); v[3] += (double)(p * p); }
+            }
+        }
+    }
+    if (PREV) block_sum_to_partials<4>(v, partials, blockIdx.y * gridDim.x + blockIdx.x);
+}
+
+// beta = max(num/den, 0) in real_t, nan -> 0 (divide_scalars_positive, utils.h:140-146); stays on the device
+template <typename R>
+__global__ void k_beta_from_sums(const double *__restrict__ sums, double *beta) {
+    if (threadIdx.x < 2) {
+        R q = (R)sums[2 * threadIdx.x] / (R)sums[2 * threadIdx.x + 1];
+        beta[threadIdx.x] = (q > (R)0) ? (double)q : 0.0;
+    }
+}
+
+// z = alpha*x + sgn*y on up to three planes in one launch; alpha either by value or read from
+// device memory (beta[which]), like the reference's axmy kernels (utils.h:97-114).
+template <typename R>
+struct Axy3 { const R *x[3]; const R *y[3]; R *z[3]; size_t n[3]; int which[3]; };
+template <typename R>
+__global__ void __launch_bounds__(256) k_axy3(Axy3<R> d, R alpha0, R alpha1, const double *__restrict__ dev_alpha, R sgn) {
+    const int pl = blockIdx.y;
+    if (!d.x[pl]) return;
+    R al = d.which[pl] ? alpha1 : alpha0;
+    if (dev_alpha) al = (R)dev_alpha[d.which[pl]];
+    const R *x = d.x[pl], *y = d.y[pl];
+    R *z = d.z[pl];
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < d.n[pl]; i += (size_t)gridDim.x * 256)
+        z[i] = al * x[i] + sgn * y[i];
+}
+
 // ----------------------------------------------------------------------------- host wrappers
 #define GRID2D(c) dim3 bdim(32, 8), gdim(((c)->g.Nx + 31) / 32, ((c)->g.j1 - (c)->g.j0 + 7) / 8)
 #define EDGE_A(buf, R) ((buf) ? (const R *)(buf)->p[0] : nullptr)
@@ -521,33 +595,94 @@ extern "C" int svl_axpy(svl_ctx *c, const svl_buf *x, const svl_buf *y, svl_buf 
 }
 
 // ----------------------------------------------------------------------------- fused CG iteration halves
-// First version: composition of the kernels above on one stream with a single host
-// synchronisation per half (the reference needs ~30 launches and several blocking reads).
+template <typename R>
+static int axy3_t(svl_ctx *c, const svl_buf *xp, const svl_buf *yp, svl_buf *zp, const svl_buf *xA, const svl_buf *yA,
+                  svl_buf *zA, double a0, double a1, const double *dev_alpha, double sgn) {
+    Axy3<R> d;
+    memset(&d, 0, sizeof(d));
+    size_t plane = (size_t)c->g.rows * c->g.P;
+    d.x[0] = (const R *)xp->p[0]; d.y[0] = (const R *)yp->p[0]; d.z[0] = (R *)zp->p[0]; d.n[0] = 2 * plane; d.which[0] = 0;
+    if (xA) {
+        for (int k = 0; k < 2; k++) {
+            d.x[1 + k] = (const R *)xA->p[k]; d.y[1 + k] = (const R *)yA->p[k]; d.z[1 + k] = (R *)zA->p[k];
+            d.n[1 + k] = plane; d.which[1 + k] = 1;
+        }
+    }
+    int nb = svl_nblocks(2 * plane, 256 * 8);
+    if (nb > 148 * 8) nb = 148 * 8;
+    k_axy3<R><<<dim3(nb, xA ? 3 : 1), 256, 0, c->stream>>>(d, (R)a0, (R)a1, dev_alpha, (R)sgn);
+    SVL_CHECK(cudaGetLastError());
+    c->stat_launches += 1;
+    return 0;
+}
+
+template <typename R>
+static int cg_begin_t(svl_ctx *c, int solveA, int have_prev, double kappa2, double eps, const svl_buf *epsf, double H,
+                      const svl_buf *psi, const svl_buf *abei, const svl_buf *ab, svl_buf *g_psi, svl_buf *g_psi_prev,
+                      svl_buf *d_psi, svl_buf *g_A, svl_buf *g_A_prev, svl_buf *d_A, double *beta, double *c_out) {
+    typedef typename V2<R>::type C;
+    GRID2D(c);
+    int nb = gdim.x * gdim.y;
+    SVL_TRY(svl_ensure_partials(c, (size_t)nb * 17));
+    const R *epf = epsf ? (const R *)epsf->p[0] : nullptr;
+#define GRAD_ARGS c->g, (R)kappa2, (R)eps, epf, (R)H, c->nf, (const C *)psi->p[0], EDGE_A(abei, R), EDGE_B(abei, R), \
+                  EDGE_A(ab, R), EDGE_B(ab, R), (C *)g_psi->p[0], solveA ? (R *)g_A->p[0] : nullptr,                 \
+                  solveA ? (R *)g_A->p[1] : nullptr, (const C *)g_psi_prev->p[0],                                    \
+                  solveA ? (const R *)g_A_prev->p[0] : nullptr, solveA ? (const R *)g_A_prev->p[1] : nullptr, c->partials
+    if (solveA && have_prev) k_cg_grad<R, true, true><<<gdim, bdim, 0, c->stream>>>(GRAD_ARGS);
+    else if (solveA) k_cg_grad<R, true, false><<<gdim, bdim, 0, c->stream>>>(GRAD_ARGS);
+    else if (have_prev) k_cg_grad<R, false, true><<<gdim, bdim, 0, c->stream>>>(GRAD_ARGS);
+    else k_cg_grad<R, false, false><<<gdim, bdim, 0, c->stream>>>(GRAD_ARGS);
+#undef GRAD_ARGS
+    SVL_CHECK(cudaGetLastError());
+    c->stat_launches += 1;
+    double *dbeta = c->d_result + 32;                 // device-resident beta[2]
+    if (have_prev) {
+        SVL_TRY(svl_finish_sum(c, nb, 4, 1.0, nullptr));          // d_result[0..3], no host read
+        k_beta_from_sums<R><<<1, 32, 0, c->stream>>>(c->d_result, dbeta);
+        SVL_CHECK(cudaGetLastError());
+        if (!solveA) { /* beta[1] unused */ }
+    } else {
+        // first iteration of a cg() call: keep the betas of the previous call (quirk Q6)
+        SVL_CHECK(cudaMemcpyAsync(dbeta, beta, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    // direction update d <- beta*d - g with beta read on the device
+    SVL_TRY(axy3_t<R>(c, d_psi, g_psi, d_psi, solveA ? d_A : nullptr, g_A, d_A, 0.0, 0.0, dbeta, -1.0));
+    // Quirk Q11: the coefficient kernels use the scalar eps (0.0 when eps is a field)
+    double eps_coef = epsf ? 0.0 : eps;
+    int rc;
+    if (solveA) rc = svl_cg_coef(c, kappa2, eps_coef, H, psi, d_psi, abei, ab, d_A, c_out);   // one host sync
+    else rc = svl_cg_coef_psi(c, kappa2, eps_coef, H, psi, d_psi, abei, ab, c_out);
+    if (rc) return rc;
+    SVL_CHECK(cudaMemcpyAsync(c->h_result + 32, dbeta, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SVL_CHECK(cudaStreamSynchronize(c->stream));
+    beta[0] = c->h_result[32];
+    if (solveA) beta[1] = c->h_result[33];
+    return 0;
+}
+
 extern "C" int svl_cg_begin(svl_ctx *c, int solveA, int have_prev, double kappa2, double eps, const svl_buf *epsf,
                             double H, const svl_buf *psi, const svl_buf *abei, const svl_buf *ab, svl_buf *g_psi,
                             svl_buf *g_psi_prev, svl_buf *d_psi, svl_buf *g_A, svl_buf *g_A_prev, svl_buf *d_A,
                             double *beta, double *c_out) {
     SVL_REQUIRE(c && beta && c_out, "null argument");
-    SVL_TRY(svl_jacobian_psi(c, kappa2, eps, epsf, H, psi, abei, ab, g_psi));
-    if (solveA) SVL_TRY(svl_jacobian_A(c, kappa2, H, psi, abei, ab, g_A));
-    if (have_prev) {
-        SVL_TRY(svl_cg_beta(c, g_psi, g_psi_prev, &beta[0]));
-        if (solveA) SVL_TRY(svl_cg_beta(c, g_A, g_A_prev, &beta[1]));
-    }
-    SVL_TRY(svl_axmy(c, d_psi, g_psi, d_psi, beta[0]));
-    if (solveA) SVL_TRY(svl_axmy(c, d_A, g_A, d_A, beta[1]));
-    // Quirk Q11: coefficient kernels use the scalar eps (0.0 when eps is a field) -- caller passes it
-    double eps_coef = epsf ? 0.0 : eps;
-    if (solveA) return svl_cg_coef(c, kappa2, eps_coef, H, psi, d_psi, abei, ab, d_A, c_out);
-    return svl_cg_coef_psi(c, kappa2, eps_coef, H, psi, d_psi, abei, ab, c_out);
+    SVL_TRY(check_state(psi, abei, ab, epsf));
+    SVL_REQUIRE(g_psi && g_psi_prev && d_psi && g_psi->kind == SVL_NODE_C && g_psi_prev->kind == SVL_NODE_C &&
+                d_psi->kind == SVL_NODE_C, "psi-side CG buffers must be SVL_NODE_C");
+    SVL_REQUIRE(!solveA || (g_A && g_A_prev && d_A && ab && g_A->kind == SVL_EDGE && g_A_prev->kind == SVL_EDGE &&
+                            d_A->kind == SVL_EDGE), "A-side CG buffers must be SVL_EDGE");
+    if (c->rsize == 4) return cg_begin_t<float>(c, solveA, have_prev, kappa2, eps, epsf, H, psi, abei, ab, g_psi, g_psi_prev,
+                                                d_psi, g_A, g_A_prev, d_A, beta, c_out);
+    return cg_begin_t<double>(c, solveA, have_prev, kappa2, eps, epsf, H, psi, abei, ab, g_psi, g_psi_prev, d_psi, g_A,
+                              g_A_prev, d_A, beta, c_out);
 }
 
 extern "C" int svl_cg_end(svl_ctx *c, int solveA, double kappa2, double eps, const svl_buf *epsf, double H, svl_buf *psi,
                           const svl_buf *abei, svl_buf *ab, const svl_buf *d_psi, const svl_buf *d_A, double alpha_psi,
                           double alpha_A, double *E_out) {
-    SVL_REQUIRE(c, "null context");
-    SVL_TRY(svl_axpy(c, d_psi, psi, psi, alpha_psi));
-    if (solveA) SVL_TRY(svl_axpy(c, d_A, ab, ab, alpha_A));
+    SVL_REQUIRE(c && psi && d_psi, "null argument");
+    if (c->rsize == 4) SVL_TRY(axy3_t<float>(c, d_psi, psi, psi, solveA ? d_A : nullptr, ab, ab, alpha_psi, alpha_A, nullptr, 1.0));
+    else SVL_TRY(axy3_t<double>(c, d_psi, psi, psi, solveA ? d_A : nullptr, ab, ab, alpha_psi, alpha_A, nullptr, 1.0));
     if (E_out) return svl_free_energy(c, kappa2, eps, epsf, H, psi, abei, ab, E_out);
     return 0;
 }
