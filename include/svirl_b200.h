@@ -53,8 +53,9 @@ int svl_create(svl_ctx **out, int device_id, int Nx, int Ny, double dx, double d
                int j0, int j1);
 int svl_destroy(svl_ctx *ctx);
 int svl_synchronize(svl_ctx *ctx);
-/* knobs: "psi_kernel" (0 = plain per-node, 1 = temporally blocked streaming), "psi_k" (sweeps
- * fused per launch), "tma" (0/1), "graphs" (0/1) */
+/* knobs: "psi_kernel" (0 = plain per-node, 1 = temporally blocked streaming, 2 = register-resident
+ * tile kernel, default), "psi_k" (psi sweeps fused per launch), "tma" (0/1), "graphs" (0/1),
+ * "a_kernel" (0 = per-node A sweep, 1 = tile kernel fusing sweep pairs, default) */
 int svl_set_option(svl_ctx *ctx, const char *name, int value);
 int svl_get_stat(svl_ctx *ctx, const char *name, double *value);
 /* CUDA events on the context's launch stream (8 slots), for device-side timing */

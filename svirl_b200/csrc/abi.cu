@@ -89,6 +89,7 @@ extern "C" int svl_create(svl_ctx **out, int device_id, int Nx, int Ny, double d
     c->opt_psi_k = 4;
     c->opt_tma = 1;
     c->opt_graphs = 1;
+    c->opt_a_kernel = 1;
     c->pred_psi = c->pred_A = c->pred_psi2 = c->pred_A2 = 0;
     *out = c;
     return svl_set_material(c, nullptr);
@@ -141,6 +142,7 @@ extern "C" int svl_set_option(svl_ctx *c, const char *name, int v) {
     else if (!strcmp(name, "psi_k")) { SVL_REQUIRE(v >= 1 && v <= SVL_HALO, "psi_k out of range"); c->opt_psi_k = v; }
     else if (!strcmp(name, "tma")) c->opt_tma = v;
     else if (!strcmp(name, "graphs")) c->opt_graphs = v;
+    else if (!strcmp(name, "a_kernel")) c->opt_a_kernel = v;
     else if (!strcmp(name, "reset_prediction")) { c->pred_psi = c->pred_A = c->pred_psi2 = c->pred_A2 = 0; }
     else { svl_set_error("unknown option %s", name); return 2; }
     return 0;

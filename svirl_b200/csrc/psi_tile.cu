@@ -317,8 +317,8 @@ struct TileIO {
 // small cache avoids six driver encode calls per launch.
 struct MapKey { const void *base; int w, rows, box_w, box_h, dt; size_t pitch; };
 struct MapEnt { MapKey k; CUtensorMap tm; };
-static int cached_map(CUtensorMap *out, CUtensorMapDataType dt, const void *base, size_t width, size_t rows,
-                      size_t pitch_bytes, int box_w, int box_h) {
+int svl_tma_map(CUtensorMap *out, CUtensorMapDataType dt, const void *base, size_t width, size_t rows,
+                size_t pitch_bytes, int box_w, int box_h) {   // also used by a_tile.cu
     static MapEnt cache[64];
     static int n = 0, next = 0;
     MapKey k = {base, (int)width, (int)rows, box_w, box_h, (int)dt, pitch_bytes};
@@ -356,12 +356,12 @@ static int launch_tile_t(svl_ctx *c, TileArgs &A, const TileIO &io) {
     static_assert(TXE * 2 <= 256, "complex double box exceeds 256 elements");
     size_t pr = (size_t)g.P * sizeof(R), pc = (size_t)g.P * sizeof(C);
     CUtensorMap tm[6];
-    SVL_TRY(cached_map(&tm[0], ct, io.psi, (size_t)g.Nx * cmul, g.rows, pc, TXE * cmul, S::EY));
-    SVL_TRY(cached_map(&tm[1], ct, io.rhs, (size_t)g.Nx * cmul, g.rows, pc, TXE * cmul, S::EY));
-    SVL_TRY(cached_map(&tm[2], rt, io.a, g.Nx, g.rows, pr, TXE, S::EY));
-    SVL_TRY(cached_map(&tm[3], rt, io.b, g.Nx, g.rows, pr, TXE, S::EY));
-    SVL_TRY(cached_map(&tm[4], rt, EPS ? io.epsf : io.a, g.Nx, g.rows, pr, TXE, S::EY));
-    SVL_TRY(cached_map(&tm[5], CU_TENSOR_MAP_DATA_TYPE_UINT8, io.nf, g.Nx, g.rows, (size_t)g.P, S::NFW, S::EY));
+    SVL_TRY(svl_tma_map(&tm[0], ct, io.psi, (size_t)g.Nx * cmul, g.rows, pc, TXE * cmul, S::EY));
+    SVL_TRY(svl_tma_map(&tm[1], ct, io.rhs, (size_t)g.Nx * cmul, g.rows, pc, TXE * cmul, S::EY));
+    SVL_TRY(svl_tma_map(&tm[2], rt, io.a, g.Nx, g.rows, pr, TXE, S::EY));
+    SVL_TRY(svl_tma_map(&tm[3], rt, io.b, g.Nx, g.rows, pr, TXE, S::EY));
+    SVL_TRY(svl_tma_map(&tm[4], rt, EPS ? io.epsf : io.a, g.Nx, g.rows, pr, TXE, S::EY));
+    SVL_TRY(svl_tma_map(&tm[5], CU_TENSOR_MAP_DATA_TYPE_UINT8, io.nf, g.Nx, g.rows, (size_t)g.P, S::NFW, S::EY));
     int ntiles = ((g.Nx + TX - 1) / TX) * ((g.j1 - g.j0 + TYO - 1) / TYO);
     int grid = ntiles < slots ? ntiles : slots;
     kern<<<grid, TXE * NB, S::total, c->stream>>>(A, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]);

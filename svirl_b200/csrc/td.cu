@@ -10,6 +10,9 @@ int svl_psi_stream_fit_k(int K);
 int svl_launch_psi_tile(svl_ctx *c, int K, double dt, double eps, const svl_buf *epsf, const svl_buf *ab,
                         const svl_buf *rhs, const svl_buf *psi, svl_buf *out, double lang_c, uint32_t rand_t,
                         unsigned long long *resid_slots);     // psi_tile.cu
+int svl_launch_a_tile(svl_ctx *c, int K, double dt, double kappa2, double rho, double H, const svl_buf *psi,
+                      const svl_buf *rhs, const svl_buf *ab, svl_buf *out, double lang_c, uint32_t rand_t,
+                      unsigned long long *resid_slots);       // a_tile.cu
 
 // ----------------------------------------------------------------------------- plain psi sweep
 // One thread per node; neighbours come through L1/L2.  NOISE: 0 none, 1 add + write back to rhs
@@ -389,22 +392,55 @@ extern "C" int svl_td_psi_solve(svl_ctx *c, double dt, double eps, const svl_buf
 }
 
 // ----------------------------------------------------------------------------- A solve
-//   in(0) = B0 (= right-hand side), in(s odd) = S1, in(s even >= 2) = S2; out(s even) = S1, out(s odd) = S2
-//   phase(s) = iterate s - (s mod 2)  (quirk Q1)  = B0 for s <= 1, else S2 (which IS out(s) for odd s).
+// The link phase of sweep s comes from iterate s - (s mod 2) (quirk Q1): for even s that is the
+// sweep's own input, which is what lets a_tile.cu fuse sweeps (2m, 2m+1) into one launch.
 struct ASolveArgs {
     double dt, kappa2, rho, H; const svl_buf *psi; double lang_c; uint32_t rand_t;
 };
 
-static int a_launch_range(svl_ctx *c, const ASolveArgs &A, svl_buf *B0, svl_buf *S1, svl_buf *S2, int s0, int s1) {
-    int noise = A.lang_c > 1.0e-32 ? 2 : 0;
-    for (int s = s0; s < s1; s++) {
-        const svl_buf *in = s == 0 ? B0 : ((s & 1) ? S1 : S2);
-        svl_buf *out = (s & 1) ? S2 : S1;
-        const svl_buf *ph = s <= 1 ? B0 : S2;
-        SVL_TRY(svl_slab_wait(c));
-        SVL_TRY(svl_launch_a_sweep(c, A.dt, A.kappa2, A.rho, A.H, A.psi, ph, B0, in, out, A.lang_c, A.rand_t, noise,
-                                   c->d_resid + s));
+// Rotation state of the A solve.  `cur` holds iterate s, `even` the newest even iterate <= s
+// (the link-phase source of sweeps s and s+1 when s is even: quirk Q1).  B0 (the caller's buffer)
+// is iterate 0 and the right-hand side and is never written.
+struct AIter {
+    svl_buf *B0, *S1, *S2;
+    svl_buf *cur, *even;
+    int s;
+    int l_s, l_K;                 // the last launch: first sweep, sweeps, and the state before it
+    svl_buf *l_cur, *l_even;
+    void reset() { cur = even = B0; s = 0; l_s = 0; l_K = 0; l_cur = l_even = B0; }
+};
+
+// Launch sweeps [it.s, upto).  Even sweeps go to the tile kernel (a_tile.cu), two per launch where
+// possible; an odd sweep can only follow a lone even one (continuation after an undershoot) and
+// takes the per-node kernel with the phase buffer aliasing the output, exactly like the reference.
+static int a_advance(svl_ctx *c, const ASolveArgs &A, AIter &it, int upto) {
+    const int noise = A.lang_c > 1.0e-32 ? 2 : 0;
+    while (it.s < upto) {
+        it.l_s = it.s; it.l_cur = it.cur; it.l_even = it.even;
+        int K = 1;
+        svl_buf *out;
+        if ((it.s & 1) == 0) {
+            out = it.cur == it.S1 ? it.S2 : it.S1;
+            if (c->opt_a_kernel >= 1) {
+                K = upto - it.s >= 2 ? 2 : 1;
+                SVL_TRY(svl_launch_a_tile(c, K, A.dt, A.kappa2, A.rho, A.H, A.psi, it.B0, it.cur, out, A.lang_c, A.rand_t,
+                                          c->d_resid + it.s));
+            } else {
+                SVL_TRY(svl_slab_wait(c));
+                SVL_TRY(svl_launch_a_sweep(c, A.dt, A.kappa2, A.rho, A.H, A.psi, it.cur, it.B0, it.cur, out, A.lang_c,
+                                           A.rand_t, noise, c->d_resid + it.s));
+            }
+            it.cur = out;
+            if (K == 2) it.even = out;
+        } else {
+            out = it.even == it.B0 ? (it.cur == it.S1 ? it.S2 : it.S1) : it.even;
+            SVL_TRY(svl_slab_wait(c));
+            SVL_TRY(svl_launch_a_sweep(c, A.dt, A.kappa2, A.rho, A.H, A.psi, it.even, it.B0, it.cur, out, A.lang_c, A.rand_t,
+                                       noise, c->d_resid + it.s));
+            it.cur = it.even = out;
+        }
         SVL_TRY(svl_slab_push_ab(c, out));
+        it.s += K; it.l_K = K;
     }
     return 0;
 }
@@ -414,9 +450,11 @@ extern "C" int svl_td_a_solve(svl_ctx *c, double dt, double kappa2, double rho, 
     SVL_REQUIRE(c, "null context");
     SVL_REQUIRE(psi && psi->kind == SVL_NODE_C, "psi must be SVL_NODE_C");
     SVL_REQUIRE(ab && ab->kind == SVL_EDGE, "ab must be SVL_EDGE");
-    svl_buf *S1, *S2;
-    SVL_TRY(svl_scratch_edge(c, 0, &S1));
-    SVL_TRY(svl_scratch_edge(c, 1, &S2));
+    AIter it;
+    it.B0 = ab;
+    SVL_TRY(svl_scratch_edge(c, 0, &it.S1));
+    SVL_TRY(svl_scratch_edge(c, 1, &it.S2));
+    it.reset();
     ASolveArgs A = {dt, kappa2, rho, H, psi, lang_c, rand_t};
     SVL_CHECK(cudaMemsetAsync(c->d_resid, 0, SVL_MAX_SWEEPS * sizeof(unsigned long long), c->stream));
     int done = 0, nstop = -1;
@@ -425,18 +463,30 @@ extern "C" int svl_td_a_solve(svl_ctx *c, double dt, double kappa2, double rho, 
         if (done == 0) upto = first_batch(c->pred_A, c->pred_A2);
         else upto = done + more_sweeps(done >= 2 ? slot_value(c->h_resid[done - 2]) : 0.0, slot_value(c->h_resid[done - 1]), stop_eps);
         if (upto > SVL_MAX_SWEEPS) upto = SVL_MAX_SWEEPS;
-        SVL_TRY(a_launch_range(c, A, ab, S1, S2, done, upto));
+        SVL_TRY(a_advance(c, A, it, upto));
         SVL_TRY(read_resid(c, done, upto - done));
         for (int s = done; s < upto; s++)
             if (stop_rule(c, slot_value(c->h_resid[s]), stop_eps)) { nstop = s + 1; break; }
         done = upto;
         if (nstop < 0 && done >= SVL_MAX_SWEEPS) nstop = SVL_MAX_SWEEPS;
     }
-    if (nstop < done - 1) {   // overshoot by more than one: replay (an overshoot by one leaves in(done-1) intact)
-        c->stat_replays += 1;
-        SVL_TRY(a_launch_range(c, A, ab, S1, S2, 0, nstop));
+    svl_buf *res = it.cur;
+    if (nstop < done) {
+        if (nstop == it.l_s && nstop > 0) {
+            res = it.l_cur;                              // the input of the last launch (still intact) is the answer
+        } else if (nstop > it.l_s) {
+            // the first sweep of the last pair converged: redo that launch as a single sweep
+            c->stat_replays += 1;
+            it.s = it.l_s; it.cur = it.l_cur; it.even = it.l_even;
+            SVL_TRY(a_advance(c, A, it, nstop));
+            res = it.cur;
+        } else {
+            c->stat_replays += 1;
+            it.reset();
+            SVL_TRY(a_advance(c, A, it, nstop));
+            res = it.cur;
+        }
     }
-    svl_buf *res = ((nstop - 1) & 1) ? S2 : S1;
     SVL_TRY(svl_slab_wait(c));
     SVL_TRY(svl_swap(c, ab, res));
     c->pred_A2 = c->pred_A;

@@ -32,11 +32,13 @@ def relerr(x, ref):
 # temporal-blocking depths, and the streaming kernel with plain-load staging
 KERNELS = [("plain", 0, 1, 1), ("stream_k4_tma", 1, 4, 1), ("stream_k1_tma", 1, 1, 1), ("stream_k3_tma", 1, 3, 1),
            ("stream_k6_tma", 1, 6, 1), ("stream_k4_ldg", 1, 4, 0),
-           ("tile_k4", 2, 4, 1), ("tile_k1", 2, 1, 1), ("tile_k3", 2, 3, 1), ("tile_k8", 2, 8, 1)]
+           ("tile_k4", 2, 4, 1), ("tile_k1", 2, 1, 1), ("tile_k3", 2, 3, 1), ("tile_k8", 2, 8, 1),
+           ("tile_k4_plainA", 2, 4, 1, 0)]        # 5th entry: A-sweep kernel (0 per-node, default 1 = pair tile kernel)
 
 
 def set_kernel(gl, kernel):
-    _, pk, k, tma = kernel
+    _, pk, k, tma = kernel[:4]
+    gl.par.set_option("a_kernel", kernel[4] if len(kernel) > 4 else 1)
     gl.par.set_option("psi_kernel", pk)
     gl.par.set_option("psi_k", k)
     gl.par.set_option("tma", tma)
@@ -179,7 +181,8 @@ def test_cg_full_first_iterations(name):
     assert np.all(np.diff(E) < 0)          # energy decreases monotonically
 
 
-@pytest.mark.parametrize("kernel", [KERNELS[0], KERNELS[1], KERNELS[6]], ids=["plain", "stream_k4_tma", "tile_k4"])
+@pytest.mark.parametrize("kernel", [KERNELS[0], KERNELS[1], KERNELS[6], KERNELS[10]],
+                         ids=["plain", "stream_k4_tma", "tile_k4", "tile_k4_plainA"])
 def test_cfg1_readme_1000_steps(kernel):
     """BASELINE configs[0]: 129^2, kappa 5, sigma 200, H 0.1, fp64, td(0.1, 1000): psi, a, b within
     1e-10, identical sweep counts, identical vortex count and positions."""
@@ -276,3 +279,30 @@ def test_stream_kernel_equals_plain_kernel_large_grid(dtype):
         if dtype is np.float64:
             assert n == out[0][1]
         assert np.abs(psi - out[0][0]).max() < tol
+
+
+@pytest.mark.parametrize("lang", [0.0, 0.05], ids=["quiet", "langevin"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_a_tile_kernel_equals_plain_kernel_large_grid(dtype, lang):
+    """The pair-fusing A-sweep tile kernel (a_tile.cu) and the per-node A kernel follow the same
+    finite-kappa trajectory on a multi-tile 700 x 517 grid with holes (same sweep counts in fp64,
+    values equal to rounding), with and without Langevin noise."""
+    from svirl_b200 import GLSolver
+    Nx, Ny = 700, 517
+    rs = np.random.RandomState(3)
+    mt = rs.rand(Nx - 1, Ny - 1) > 0.15
+    out = []
+    for ak in (0, 1):
+        gl = GLSolver(Nx=Nx, Ny=Ny, dx=0.5, dy=0.4, dtype=dtype, gl_parameter=2.0, normal_conductivity=10.0,
+                      homogeneous_external_field=0.1, random_seed=5, material_tiling=mt,
+                      order_parameter_Langevin_coefficient=lang, vector_potential_Langevin_coefficient=lang)
+        gl.par.set_option("a_kernel", ak)
+        gl.solve.td(dt=0.1, Nt=12)
+        a, b = gl.vars.vector_potential
+        out.append((gl.vars.order_parameter, a, b, gl.solve._td.sweeps_vector_potential, gl.par.stat("replays")))
+        gl.par.close()
+    tol = 1e-12 if dtype is np.float64 else 2e-5
+    if dtype is np.float64:
+        assert out[0][3] == out[1][3]
+    for k in range(3):
+        assert np.abs(out[0][k] - out[1][k]).max() < tol
