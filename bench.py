@@ -268,6 +268,7 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--psi-kernel", type=int, default=None)
     ap.add_argument("--psi-k", type=int, default=None)
+    ap.add_argument("--a-kernel", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -311,6 +312,8 @@ def main():
         par.set_option("psi_kernel", args.psi_kernel)
     if args.psi_k is not None:
         par.set_option("psi_k", args.psi_k)
+    if args.a_kernel is not None:
+        par.set_option("a_kernel", args.a_kernel)
     td_kw = dict(dt=0.1)
     if wl.get("cg"):
         return bench_cg(args, wl, gl, par, N)

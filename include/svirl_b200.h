@@ -55,9 +55,12 @@ int svl_destroy(svl_ctx *ctx);
 int svl_synchronize(svl_ctx *ctx);
 /* knobs: "psi_kernel" (0 = plain per-node, 1 = temporally blocked streaming, 2 = register-resident
  * tile kernel, default), "psi_k" (psi sweeps fused per launch), "tma" (0/1), "graphs" (0/1),
- * "a_kernel" (0 = per-node A sweep, 1 = tile kernel fusing sweep pairs, default) */
+ * "a_kernel" (0 = per-node A sweep, 1..4 = tile kernel fusing sweep pairs in four layouts, default 2),
+ * "cg_fused" (1 = three-pass CG iteration, default; 0 = composition of the single kernels) */
 int svl_set_option(svl_ctx *ctx, const char *name, int value);
 int svl_get_stat(svl_ctx *ctx, const char *name, double *value);
+/* self-test hook: the library's own sincos (used for every link variable exp(-i d A)) on n values */
+int svl_debug_sincos(svl_ctx *ctx, size_t n, const double *x, double *s_out, double *c_out);
 /* CUDA events on the context's launch stream (8 slots), for device-side timing */
 int svl_event_record(svl_ctx *ctx, int slot);
 int svl_event_elapsed_ms(svl_ctx *ctx, int slot0, int slot1, double *ms);

@@ -22,6 +22,7 @@ SIGNATURES = {
     "svl_synchronize": ([_p], _i),
     "svl_set_option": ([_p, C.c_char_p, _i], _i),
     "svl_get_stat": ([_p, C.c_char_p, _pd], _i),
+    "svl_debug_sincos": ([_p, _sz, _pd, _pd, _pd], _i),
     "svl_event_record": ([_p, _i], _i),
     "svl_event_elapsed_ms": ([_p, _i, _i, _pd], _i),
     "svl_alloc": ([_p, _i, _sz, _i, C.POINTER(_p)], _i),

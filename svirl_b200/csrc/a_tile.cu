@@ -18,6 +18,7 @@
 // node for two sweeps, against 2 x (9R+1) for two single sweeps.
 #include "common.cuh"
 #include <cuda.h>
+#include <type_traits>
 
 int svl_tma_map(CUtensorMap *out, CUtensorMapDataType dt, const void *base, size_t width, size_t rows,
                 size_t pitch_bytes, int box_w, int box_h);   // psi_tile.cu
@@ -63,8 +64,8 @@ struct ASmem {
     static constexpr uint32_t tx_bytes = (uint32_t)((sizeof(C) + 2 * sizeof(R)) * NN);
 };
 
-template <typename R, int K, int TXE, int V, int NB>
-__global__ void __launch_bounds__(TXE *NB, 2)
+template <typename R, int K, int TXE, int V, int NB, int MODE>
+__global__ void __launch_bounds__(TXE *NB, (TXE * NB > 256 ? 1 : 2))
 k_a_tile(const __grid_constant__ ATileArgs A, const __grid_constant__ CUtensorMap tm_psi,
          const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b) {
     typedef typename V2<R>::type C;
@@ -119,19 +120,24 @@ k_a_tile(const __grid_constant__ ATileArgs A, const __grid_constant__ CUtensorMa
     const R inv_da = (R)1.0 / ((R)1.0 + (R)2.0 * dtrk * idy2), inv_db = (R)1.0 / ((R)1.0 + (R)2.0 * dtrk * idx2);
     const R kH2 = (R)2.0 * (R)A.kappa2 * (R)A.H;
     const bool xin = x >= 0 && x < g.Nx;
-    R qa[V], qb[V];
+    // c starts as the right-hand side q (own edges, straight from global memory: coalesced along x,
+    // overlapping the TMA) and becomes  c = q + dt*rho*(js + rh)  below
+    R ca[V], cb[V];
     unsigned fl[V];
+    auto load_rhs = [&]() {
 #pragma unroll
-    for (int v = 0; v < V; v++) {
-        const int y = yg0 + r0 + v, pr = y - g.rb;
-        qa[v] = 0; qb[v] = 0; fl[v] = 0;
-        if (xin && pr >= 0 && pr < g.rows) {
-            const size_t n = (size_t)pr * g.P + x;
-            qa[v] = ((const R *)A.rhs_a)[n];
-            qb[v] = ((const R *)A.rhs_b)[n];
-            fl[v] = A.nf[n];
+        for (int v = 0; v < V; v++) {
+            const int pr = yg0 + r0 + v - g.rb;
+            ca[v] = 0; cb[v] = 0; fl[v] = 0;
+            if (xin && pr >= 0 && pr < g.rows) {
+                const size_t n = (size_t)pr * g.P + x;
+                ca[v] = ((const R *)A.rhs_a)[n];
+                cb[v] = ((const R *)A.rhs_b)[n];
+                fl[v] = A.nf[n];
+            }
         }
-    }
+    };
+    load_rhs();
     // ---- wait for the boxes: one warp polls, the barrier releases the rest
     if (tid < 32) {
         uint32_t ok = 0;
@@ -144,31 +150,54 @@ k_a_tile(const __grid_constant__ ATileArgs A, const __grid_constant__ CUtensorMa
     __syncthreads();
 
     // ---- per-edge constants  c = q + dt*rho*(js + rh)   (td.h:366-405, 412-451)
-    R Av[V], Bv[V], ca[V], cb[V];
     // boundary doubling of the b-edge depends on the column only
     const R rh_b = x == 0 ? -kH2 * idx : (x == g.Nx - 1 ? kH2 * idx : (R)0);
     const R wb = dtrk * ((x == 0 || x == g.Nx - 1) ? (R)2 : (R)1);
+    // The fast pass evaluates all 2V link variables with the branch-free sincos core (the independent
+    // polynomials interleave) and notes whether any phase was outside its range; only then the
+    // constants are redone through libdevice.
+    bool bad = false;
+    auto constants = [&](auto fastpath) {
 #pragma unroll
-    for (int v = 0; v < V; v++) {
-        const int r = r0 + v, si = r * TXE + col, y = yg0 + r;
-        const C p0 = spsi[si], pE = spsi[si + 1], pN = spsi[si + TXE];
-        const R a0 = sa0[si], b0 = sb0[si];
-        R q_a = qa[v], q_b = qb[v];
-        if (A.noise) {      // Langevin term: added to the right-hand side on sweep 0 (td.h:370-373, 416-419)
-            const R lang = (R)A.lang_c;
-            const uint32_t na = (uint32_t)x + (uint32_t)(g.Nx - 1) * (uint32_t)y;
-            const uint32_t nb = (uint32_t)((size_t)(g.Nx - 1) * g.Ny) + (uint32_t)x + (uint32_t)g.Nx * (uint32_t)y;
-            q_a += lang * (rand_1<R>(na, A.rand_t) - (R)0.5);
-            q_b += lang * (rand_2<R>(nb, A.rand_t) - (R)0.5);
+        for (int v = 0; v < V; v++) {
+            const int r = r0 + v, si = r * TXE + col, y = yg0 + r;
+            const C p0 = spsi[si], pE = spsi[si + 1], pN = spsi[si + TXE];
+            const R pha = dx * sa0[si], phb = dy * sb0[si];
+            if (A.noise) {      // Langevin term: added to the right-hand side on sweep 0 (td.h:370-373, 416-419)
+                const R lang = (R)A.lang_c;
+                const uint32_t na = (uint32_t)x + (uint32_t)(g.Nx - 1) * (uint32_t)y;
+                const uint32_t nb = (uint32_t)((size_t)(g.Nx - 1) * g.Ny) + (uint32_t)x + (uint32_t)g.Nx * (uint32_t)y;
+                ca[v] += lang * (rand_1<R>(na, A.rand_t) - (R)0.5);
+                cb[v] += lang * (rand_2<R>(nb, A.rand_t) - (R)0.5);
+            }
+            R sa, cA, sb, cB;
+            if (decltype(fastpath)::value == 1) {
+                bad = bad || !sincos_fast_ok(pha) || !sincos_fast_ok(phb);
+                sincos_fast(pha, &sa, &cA); sincos_fast(phb, &sb, &cB);
+            } else if (decltype(fastpath)::value == 2) {       // range test per link (no interleaving)
+                sincos_r<R>(pha, &sa, &cA); sincos_r<R>(phb, &sb, &cB);
+            } else {
+                sincos_any(pha, &sa, &cA); sincos_any(phb, &sb, &cB);
+            }
+            // Im(conj(p0) U(ph) p1) = (p0 x p1) cos - (p0 . p1) sin   (svirl/cuda/common.h:65-73)
+            R jla = idx * ((p0.x * pE.y - p0.y * pE.x) * cA - (p0.x * pE.x + p0.y * pE.y) * sa);
+            R jlb = idy * ((p0.x * pN.y - p0.y * pN.x) * cB - (p0.x * pN.x + p0.y * pN.y) * sb);
+            if (!(fl[v] & (NF_PM | NF_PP))) jla = 0;
+            if (!(fl[v] & (NF_MP | NF_PP))) jlb = 0;
+            const R rh_a = y == 0 ? kH2 * idy : (y == g.Ny - 1 ? -kH2 * idy : (R)0);
+            ca[v] = ca[v] + dt_rho * (jla + rh_a);
+            cb[v] = cb[v] + dt_rho * (jlb + rh_b);
         }
-        R jla = 0, jlb = 0;
-        if (fl[v] & (NF_PM | NF_PP)) jla = idx * js_link<R, C>(p0, dx * a0, pE);
-        if (fl[v] & (NF_MP | NF_PP)) jlb = idy * js_link<R, C>(p0, dy * b0, pN);
-        const R rh_a = y == 0 ? kH2 * idy : (y == g.Ny - 1 ? -kH2 * idy : (R)0);
-        ca[v] = q_a + dt_rho * (jla + rh_a);
-        cb[v] = q_b + dt_rho * (jlb + rh_b);
-        Av[v] = a0; Bv[v] = b0;
+    };
+    if (MODE == 1) {
+        constants(std::true_type());
+        if (bad) { load_rhs(); constants(std::false_type()); }
+    } else {
+        constants(std::integral_constant<int, 2>());
     }
+    R Av[V], Bv[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) { Av[v] = sa0[(r0 + v) * TXE + col]; Bv[v] = sb0[(r0 + v) * TXE + col]; }
 
     const bool cin = col >= H && col < TXE - H && x < g.Nx;
     unsigned inmask = 0;                 // bit v: node v of this thread is an output node of the tile
@@ -236,7 +265,7 @@ k_a_tile(const __grid_constant__ ATileArgs A, const __grid_constant__ CUtensorMa
     }
 }
 
-template <typename R, int K, int TXE, int V, int NB>
+template <typename R, int K, int TXE, int V, int NB, int MODE>
 static int launch_a_tile_t(svl_ctx *c, ATileArgs &A, const void *psi, const void *a, const void *b) {
     typedef typename V2<R>::type C;
     typedef ASmem<R, TXE, V, NB> S;
@@ -244,7 +273,7 @@ static int launch_a_tile_t(svl_ctx *c, ATileArgs &A, const void *psi, const void
     constexpr int H = sizeof(R) == 8 ? 2 : 4;
     constexpr int TX = TXE - 2 * H, TYO = S::EY - 2 * K;
     static_assert(S::guard >= (TXE + 1) * sizeof(R), "guard too small");
-    auto kern = k_a_tile<R, K, TXE, V, NB>;
+    auto kern = k_a_tile<R, K, TXE, V, NB, MODE>;
     static bool configured = false;
     if (!configured) {
         SVL_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total));
@@ -284,10 +313,21 @@ int svl_launch_a_tile(svl_ctx *c, int K, double dt, double kappa2, double rho, d
         A.wait_flags = c->flags; A.wait_epoch = svl_slab_epoch(c); A.has_lo = c->has_lo; A.has_hi = c->has_hi;
         svl_slab_mark_waited(c);
     }
-    if (c->rsize == 4) {
-        if (K == 2) return launch_a_tile_t<float, 2, 64, 8, 4>(c, A, psi->p[0], ab->p[0], ab->p[1]);
-        return launch_a_tile_t<float, 1, 64, 8, 4>(c, A, psi->p[0], ab->p[0], ab->p[1]);
+    const void *P_ = psi->p[0], *a_ = ab->p[0], *b_ = ab->p[1];
+    // a_kernel option: 1 = 64x32 tile, 8 rows per thread, 2 CTAs/SM (default); 2 = same with the
+    // interleaved sincos pass; 3 / 4 = 4 rows per thread, 512 threads (per-link / interleaved)
+#define A_TILE_CASE(R_, K_) \
+    switch (c->opt_a_kernel) { \
+        case 2: return launch_a_tile_t<R_, K_, 64, 8, 4, 1>(c, A, P_, a_, b_); \
+        case 3: return launch_a_tile_t<R_, K_, 64, 4, 8, 0>(c, A, P_, a_, b_); \
+        case 4: return launch_a_tile_t<R_, K_, 64, 4, 8, 1>(c, A, P_, a_, b_); \
+        default: return launch_a_tile_t<R_, K_, 64, 8, 4, 0>(c, A, P_, a_, b_); \
     }
-    if (K == 2) return launch_a_tile_t<double, 2, 64, 8, 4>(c, A, psi->p[0], ab->p[0], ab->p[1]);
-    return launch_a_tile_t<double, 1, 64, 8, 4>(c, A, psi->p[0], ab->p[0], ab->p[1]);
+    if (c->rsize == 4) {
+        if (K == 2) A_TILE_CASE(float, 2)
+        A_TILE_CASE(float, 1)
+    }
+    if (K == 2) A_TILE_CASE(double, 2)
+    A_TILE_CASE(double, 1)
+#undef A_TILE_CASE
 }

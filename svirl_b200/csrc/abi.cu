@@ -89,7 +89,8 @@ extern "C" int svl_create(svl_ctx **out, int device_id, int Nx, int Ny, double d
     c->opt_psi_k = 4;
     c->opt_tma = 1;
     c->opt_graphs = 1;
-    c->opt_a_kernel = 1;
+    c->opt_a_kernel = 2;
+    c->opt_cg_fused = 1;
     c->pred_psi = c->pred_A = c->pred_psi2 = c->pred_A2 = 0;
     *out = c;
     return svl_set_material(c, nullptr);
@@ -143,6 +144,7 @@ extern "C" int svl_set_option(svl_ctx *c, const char *name, int v) {
     else if (!strcmp(name, "tma")) c->opt_tma = v;
     else if (!strcmp(name, "graphs")) c->opt_graphs = v;
     else if (!strcmp(name, "a_kernel")) c->opt_a_kernel = v;
+    else if (!strcmp(name, "cg_fused")) c->opt_cg_fused = v;
     else if (!strcmp(name, "reset_prediction")) { c->pred_psi = c->pred_A = c->pred_psi2 = c->pred_A2 = 0; }
     else { svl_set_error("unknown option %s", name); return 2; }
     return 0;
@@ -324,6 +326,7 @@ extern "C" int svl_swap(svl_ctx *c, svl_buf *x, svl_buf *y) {
     SVL_REQUIRE(x->kind == y->kind && x->bytes[0] == y->bytes[0] && x->bytes[1] == y->bytes[1],
                 "swap: buffers differ in kind/size");
     for (int k = 0; k < 2; k++) { void *t = x->p[k]; x->p[k] = y->p[k]; y->p[k] = t; }
+    int b = x->borrowed; x->borrowed = y->borrowed; y->borrowed = b;     // ownership travels with the storage
     return 0;
 }
 
@@ -336,5 +339,32 @@ int svl_scratch_node(svl_ctx *c, int k, svl_buf **out) {
 int svl_scratch_edge(svl_ctx *c, int k, svl_buf **out) {
     if (!c->ab_s[k]) SVL_TRY(svl_alloc(c, SVL_EDGE, 0, 0, &c->ab_s[k]));
     *out = c->ab_s[k];
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- self-test hook
+// The library's own sincos (common.cuh) evaluated on n host values: lets the tests bound its
+// error against the host libm without going through a solver.
+template <typename R>
+__global__ void k_debug_sincos(const double *x, double *s, double *c, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    R ss, cc;
+    sincos_r<R>((R)x[i], &ss, &cc);
+    s[i] = (double)ss; c[i] = (double)cc;
+}
+
+extern "C" int svl_debug_sincos(svl_ctx *c, size_t n, const double *x, double *s_out, double *c_out) {
+    SVL_REQUIRE(c && x && s_out && c_out && n > 0, "bad argument");
+    double *d = nullptr;
+    SVL_CHECK(cudaMalloc(&d, 3 * n * sizeof(double)));
+    SVL_CHECK(cudaMemcpyAsync(d, x, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (c->rsize == 4) k_debug_sincos<float><<<svl_nblocks(n, 256), 256, 0, c->stream>>>(d, d + n, d + 2 * n, n);
+    else k_debug_sincos<double><<<svl_nblocks(n, 256), 256, 0, c->stream>>>(d, d + n, d + 2 * n, n);
+    SVL_CHECK(cudaGetLastError());
+    SVL_CHECK(cudaMemcpyAsync(s_out, d + n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SVL_CHECK(cudaMemcpyAsync(c_out, d + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SVL_CHECK(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
     return 0;
 }

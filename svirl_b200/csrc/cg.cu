@@ -595,6 +595,15 @@ extern "C" int svl_axpy(svl_ctx *c, const svl_buf *x, const svl_buf *y, svl_buf 
 }
 
 // ----------------------------------------------------------------------------- fused CG iteration halves
+// cg_fused.cu: three-pass iteration (default); the composition below is kept as a cross-check
+// (option "cg_fused" = 0)
+int svl_cgf_begin(svl_ctx *c, int solveA, int have_prev, double kappa2, double eps, const svl_buf *epsf, double H,
+                  const svl_buf *psi, const svl_buf *abei, const svl_buf *ab, svl_buf *g_psi, svl_buf *g_psi_prev,
+                  svl_buf *d_psi, svl_buf *g_A, svl_buf *g_A_prev, svl_buf *d_A, double *beta, double *c_out);
+int svl_cgf_end(svl_ctx *c, int solveA, double kappa2, double eps, const svl_buf *epsf, double H, svl_buf *psi,
+                const svl_buf *abei, svl_buf *ab, const svl_buf *d_psi, const svl_buf *d_A, double alpha_psi,
+                double alpha_A, double *E_out);
+
 template <typename R>
 static int axy3_t(svl_ctx *c, const svl_buf *xp, const svl_buf *yp, svl_buf *zp, const svl_buf *xA, const svl_buf *yA,
                   svl_buf *zA, double a0, double a1, const double *dev_alpha, double sgn) {
@@ -671,6 +680,9 @@ extern "C" int svl_cg_begin(svl_ctx *c, int solveA, int have_prev, double kappa2
                 d_psi->kind == SVL_NODE_C, "psi-side CG buffers must be SVL_NODE_C");
     SVL_REQUIRE(!solveA || (g_A && g_A_prev && d_A && ab && g_A->kind == SVL_EDGE && g_A_prev->kind == SVL_EDGE &&
                             d_A->kind == SVL_EDGE), "A-side CG buffers must be SVL_EDGE");
+    if (c->opt_cg_fused)
+        return svl_cgf_begin(c, solveA, have_prev, kappa2, eps, epsf, H, psi, abei, ab, g_psi, g_psi_prev, d_psi, g_A,
+                             g_A_prev, d_A, beta, c_out);
     if (c->rsize == 4) return cg_begin_t<float>(c, solveA, have_prev, kappa2, eps, epsf, H, psi, abei, ab, g_psi, g_psi_prev,
                                                 d_psi, g_A, g_A_prev, d_A, beta, c_out);
     return cg_begin_t<double>(c, solveA, have_prev, kappa2, eps, epsf, H, psi, abei, ab, g_psi, g_psi_prev, d_psi, g_A,
@@ -681,6 +693,10 @@ extern "C" int svl_cg_end(svl_ctx *c, int solveA, double kappa2, double eps, con
                           const svl_buf *abei, svl_buf *ab, const svl_buf *d_psi, const svl_buf *d_A, double alpha_psi,
                           double alpha_A, double *E_out) {
     SVL_REQUIRE(c && psi && d_psi, "null argument");
+    SVL_TRY(check_state(psi, abei, ab, epsf));
+    SVL_REQUIRE(d_psi->kind == SVL_NODE_C && (!solveA || (d_A && ab && d_A->kind == SVL_EDGE)), "bad direction buffers");
+    if (c->opt_cg_fused)
+        return svl_cgf_end(c, solveA, kappa2, eps, epsf, H, psi, abei, ab, d_psi, d_A, alpha_psi, alpha_A, E_out);
     if (c->rsize == 4) SVL_TRY(axy3_t<float>(c, d_psi, psi, psi, solveA ? d_A : nullptr, ab, ab, alpha_psi, alpha_A, nullptr, 1.0));
     else SVL_TRY(axy3_t<double>(c, d_psi, psi, psi, solveA ? d_A : nullptr, ab, ab, alpha_psi, alpha_A, nullptr, 1.0));
     if (E_out) return svl_free_energy(c, kappa2, eps, epsf, H, psi, abei, ab, E_out);

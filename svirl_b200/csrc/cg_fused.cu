@@ -1,0 +1,569 @@
+// One CG iteration in three passes over HBM (fused lower bound ~ 40R+3 bytes/node
+// against 84R+4 as written in svirl/solvers/cg.py:238-551):
+//
+//   k_cgf_grad    Jacobians dG/dpsi, dG/dA at (psi, A)  + the four Polak-Ribiere sums
+//                 (cg.h:16-301, utils.h:13-70)
+//   k_cgf_coef    direction update d <- beta d - g (beta read on the device) fused with the 5 / 17
+//                 line-search coefficients of G(psi + a_psi d_psi, A + a_A d_A)
+//                 (utils.h:97-114, cg.h:315-731)
+//   k_cgf_update  psi <- psi + a_psi d_psi, A <- A + a_A d_A fused with the free energy of the new
+//                 state (utils.h:74-92, observables.h:251-362)
+//
+// All three walk the grid the same way: a warp owns 32 consecutive columns and a strip of V rows;
+// the lanes hold one node each, the E/W neighbours come from warp shuffles (the two edge lanes load
+// theirs), the N neighbour is the next row of the strip (one row of look-ahead), the S neighbour the
+// previous one.  Every link variable exp(-i d A) is evaluated once by the node that owns the edge
+// (2 sincos per node instead of 6 in the Jacobians) and never stored.  CTAs are persistent
+// (tile = 32 columns x 8V rows, tiles dealt round-robin), reductions accumulate in double in
+// registers across all tiles of a CTA and are reduced once per CTA in a fixed order, so the sums are
+// run-to-run reproducible and the second stage adds ~1200 partials instead of one per 256 nodes.
+// Updated fields are written out of place (a neighbour's old value must stay readable) and the
+// caller swaps storage.
+#include "common.cuh"
+
+#define CGF_V 8
+#define CGF_WARPS 8
+#define CGF_THREADS (32 * CGF_WARPS)
+#define FULL 0xffffffffu
+
+template <typename R> struct CgfState {     // what all three kernels read
+    Geo g;
+    R kappa2, eps, H;
+    const R *epsf;
+    const uint8_t *nf;
+    const typename V2<R>::type *psi;
+    const R *ae, *be, *a, *b;
+};
+
+template <typename C> __device__ __forceinline__ C shfl_down_c(C v) {
+    C r;
+    r.x = __shfl_down_sync(FULL, v.x, 1);
+    r.y = __shfl_down_sync(FULL, v.y, 1);
+    return r;
+}
+template <typename C> __device__ __forceinline__ C shfl_up_c(C v) {
+    C r;
+    r.x = __shfl_up_sync(FULL, v.x, 1);
+    r.y = __shfl_up_sync(FULL, v.y, 1);
+    return r;
+}
+template <typename R> __device__ __forceinline__ void du_w(unsigned f, R &wW, R &wE, R &wS, R &wN, R &gw) {
+    R mm = (f & NF_MM) ? (R)1 : (R)0, mp = (f & NF_MP) ? (R)1 : (R)0;
+    R pm = (f & NF_PM) ? (R)1 : (R)0, pp = (f & NF_PP) ? (R)1 : (R)0;
+    wW = (R)0.5 * (mm + mp); wE = (R)0.5 * (pm + pp);
+    wS = (R)0.5 * (mm + pm); wN = (R)0.5 * (mp + pp);
+    gw = (R)0.25 * (wW + wE + wS + wN);
+}
+// psi1 * U(ph) - psi0 with (s, c) = sincos(ph)   (cg.h:305-311)
+template <typename R, typename C> __device__ __forceinline__ C gradc(C p0, R s, R c, C p1) {
+    C z;
+    z.x = p1.x * c + p1.y * s - p0.x;
+    z.y = p1.y * c - p1.x * s - p0.y;
+    return z;
+}
+
+// tile walk shared by the three kernels
+#define CGF_TILE_LOOP_BEGIN                                                                        \
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;                                    \
+    const int ntx = (g.Nx + 31) / 32, RT = CGF_WARPS * CGF_V;                                      \
+    const int nty = (g.j1 - g.j0 + RT - 1) / RT;                                                   \
+    for (int t = blockIdx.x; t < ntx * nty; t += gridDim.x) {                                      \
+        const int i = (t % ntx) * 32 + lane;                                                       \
+        const int ys = g.j0 + (t / ntx) * RT + warp * CGF_V;                                       \
+        if (ys >= g.j1) continue;                                                                  \
+        const int ye = ys + CGF_V < g.j1 ? ys + CGF_V : g.j1;                                      \
+        const bool in = i < g.Nx;
+#define CGF_TILE_LOOP_END }
+
+// ============================================================================= update + energy
+template <typename R> struct RowU { typename V2<R>::type p; R a, b, ea, eb; };
+
+template <typename R, bool SOLVEA>
+__global__ void __launch_bounds__(CGF_THREADS, 2)
+k_cgf_update(CgfState<R> S, const typename V2<R>::type *__restrict__ dpsi, const R *__restrict__ da,
+             const R *__restrict__ db, R alpha_psi, R alpha_A, typename V2<R>::type *__restrict__ psi_out,
+             R *__restrict__ a_out, R *__restrict__ b_out, double *partials) {
+    typedef typename V2<R>::type C;
+    const Geo &g = S.g;
+    const R dx = (R)g.dx, dy = (R)g.dy, idx = (R)g.idx, idy = (R)g.idy, idx2 = (R)g.idx2, idy2 = (R)g.idy2;
+    double acc[1] = {0.0};
+    // updated state of node (ii, y); zero outside the grid (rows are always inside the plane)
+    auto load = [&](int ii, int y) {
+        RowU<R> r;
+        r.p.x = 0; r.p.y = 0; r.a = 0; r.b = 0; r.ea = 0; r.eb = 0;
+        if (ii < g.Nx) {
+            const size_t n = g.at(ii, y);
+            const C p = S.psi[n], d = dpsi[n];
+            r.p.x = alpha_psi * d.x + p.x; r.p.y = alpha_psi * d.y + p.y;
+            if (S.a) {
+                r.a = S.a[n]; r.b = S.b[n];
+                if (SOLVEA) { r.a = alpha_A * da[n] + r.a; r.b = alpha_A * db[n] + r.b; }
+            }
+            if (S.ae) { r.ea = S.ae[n]; r.eb = S.be[n]; }
+        }
+        return r;
+    };
+    CGF_TILE_LOOP_BEGIN
+        RowU<R> cur = load(i, ys);
+        for (int y = ys; y < ye; y++) {
+            const RowU<R> nxt = load(i, y + 1);
+            C pE = shfl_down_c<C>(cur.p);
+            R bE = __shfl_down_sync(FULL, cur.b, 1), ebE = __shfl_down_sync(FULL, cur.eb, 1);
+            if (lane == 31) { const RowU<R> e = load(i + 1, y); pE = e.p; bE = e.b; ebE = e.eb; }
+            if (in) {
+                const size_t n = g.at(i, y);
+                const unsigned f = S.nf[n];
+                const R eps = S.epsf ? S.epsf[n] : S.eps;
+                R e = 0;
+                if (f) {
+                    R wW, wE, wS, wN, gw;
+                    du_w<R>(f, wW, wE, wS, wN, gw);
+                    const R p2 = cur.p.x * cur.p.x + cur.p.y * cur.p.y;
+                    e += gw * ((R)0.5 * p2 - eps) * p2;
+                    R s, c;
+                    if (f & (NF_PM | NF_PP)) {
+                        sincos_r<R>(dx * (S.ae ? cur.ea + cur.a : cur.a), &s, &c);
+                        const C z = gradc<R, C>(cur.p, s, c, pE);
+                        e += wE * idx2 * (z.x * z.x + z.y * z.y);
+                    }
+                    if (f & (NF_MP | NF_PP)) {
+                        sincos_r<R>(dy * (S.ae ? cur.eb + cur.b : cur.b), &s, &c);
+                        const C z = gradc<R, C>(cur.p, s, c, nxt.p);
+                        e += wN * idy2 * (z.x * z.x + z.y * z.y);
+                    }
+                }
+                if (S.kappa2 > (R)0 && i < g.Nx - 1 && y < g.Ny - 1) {
+                    R dB = -S.H;
+                    if (S.ae) dB += idx * (ebE - cur.eb) - idy * (nxt.ea - cur.ea);
+                    if (S.a) dB += idx * (bE - cur.b) - idy * (nxt.a - cur.a);
+                    e += S.kappa2 * dB * dB;
+                }
+                acc[0] += (double)e;
+                psi_out[n] = cur.p;
+                if (SOLVEA) { a_out[n] = cur.a; b_out[n] = cur.b; }
+            }
+            cur = nxt;
+        }
+    CGF_TILE_LOOP_END
+    block_sum_to_partials<1>(acc, partials, blockIdx.x);
+}
+
+// ============================================================================= direction + coefficients
+template <typename R> struct RowD { typename V2<R>::type p, d; R a, b, ea, eb, da, db; };
+
+// NV = 5: c0..c4 (cg.h:400-467); NV = 17: c00..c04, c10..c14, c20..c24, c30, c40 (cg.h:528-701).
+// Quirk Q11: the coefficient kernels use the scalar eps only.
+template <typename R, int NV>
+__global__ void __launch_bounds__(CGF_THREADS, 2)
+k_cgf_coef(CgfState<R> S, const double *__restrict__ beta, const typename V2<R>::type *__restrict__ gpsi,
+           const R *__restrict__ ga, const R *__restrict__ gb, const typename V2<R>::type *__restrict__ dpsi_old,
+           const R *__restrict__ da_old, const R *__restrict__ db_old, typename V2<R>::type *__restrict__ dpsi_new,
+           R *__restrict__ da_new, R *__restrict__ db_new, double *partials) {
+    typedef typename V2<R>::type C;
+    constexpr bool SOLVEA = NV == 17;
+    const Geo &g = S.g;
+    const R dx = (R)g.dx, dy = (R)g.dy, idx = (R)g.idx, idy = (R)g.idy, idx2 = (R)g.idx2, idy2 = (R)g.idy2;
+    const R beta_psi = (R)beta[0], beta_A = (R)beta[1];
+    const int C1 = NV == 17 ? 5 : 1, C2 = NV == 17 ? 10 : 2, C3 = NV == 17 ? 15 : 3, C4 = NV == 17 ? 16 : 4;
+    double v[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) v[k] = 0.0;
+    auto load = [&](int ii, int y) {
+        RowD<R> r;
+        r.p.x = 0; r.p.y = 0; r.d.x = 0; r.d.y = 0; r.a = 0; r.b = 0; r.ea = 0; r.eb = 0; r.da = 0; r.db = 0;
+        if (ii < g.Nx) {
+            const size_t n = g.at(ii, y);
+            r.p = S.psi[n];
+            const C d = dpsi_old[n], gj = gpsi[n];
+            r.d.x = beta_psi * d.x - gj.x; r.d.y = beta_psi * d.y - gj.y;      // axmy_c (utils.h:97-104)
+            if (S.a) { r.a = S.a[n]; r.b = S.b[n]; }
+            if (S.ae) { r.ea = S.ae[n]; r.eb = S.be[n]; }
+            if (SOLVEA) { r.da = beta_A * da_old[n] - ga[n]; r.db = beta_A * db_old[n] - gb[n]; }
+        }
+        return r;
+    };
+    CGF_TILE_LOOP_BEGIN
+        RowD<R> cur = load(i, ys);
+        for (int y = ys; y < ye; y++) {
+            const RowD<R> nxt = load(i, y + 1);
+            C pE = shfl_down_c<C>(cur.p), dE = shfl_down_c<C>(cur.d);
+            R bE = __shfl_down_sync(FULL, cur.b, 1), ebE = __shfl_down_sync(FULL, cur.eb, 1);
+            R dbE = __shfl_down_sync(FULL, cur.db, 1);
+            if (lane == 31) {
+                const RowD<R> e = load(i + 1, y);
+                pE = e.p; dE = e.d; bE = e.b; ebE = e.eb; dbE = e.db;
+            }
+            if (in) {
+                const size_t n = g.at(i, y);
+                const unsigned f = S.nf[n];
+                if (f) {
+                    R wW, wE, wS, wN, gw;
+                    du_w<R>(f, wW, wE, wS, wN, gw);
+                    const C p0 = cur.p, d0 = cur.d;
+                    const R p2 = p0.x * p0.x + p0.y * p0.y, d2 = d0.x * d0.x + d0.y * d0.y;
+                    const R tw = (R)2.0 * (p0.x * d0.x + p0.y * d0.y);
+                    v[0] += (double)(gw * ((R)0.5 * p2 - S.eps) * p2);
+                    v[C1] += (double)(gw * tw * (p2 - S.eps));
+                    v[C2] += (double)(gw * (-S.eps * d2 + (R)0.5 * tw * tw + p2 * d2));
+                    v[C3] += (double)(gw * tw * d2);
+                    v[C4] += (double)(gw * (R)0.5 * d2 * d2);
+#pragma unroll
+                    for (int dir = 0; dir < 2; dir++) {
+                        const bool on = dir == 0 ? (f & (NF_PM | NF_PP)) : (f & (NF_MP | NF_PP));
+                        if (!on) continue;
+                        const R w = dir == 0 ? wE : wN, i2 = dir == 0 ? idx2 : idy2, d = dir == 0 ? dx : dy;
+                        R ph = 0;
+                        if (S.ae) ph += d * (dir == 0 ? cur.ea : cur.eb);
+                        if (S.a) ph += d * (dir == 0 ? cur.a : cur.b);
+                        R s, c;
+                        sincos_r<R>(ph, &s, &c);
+                        const C p1 = dir == 0 ? pE : nxt.p, d1 = dir == 0 ? dE : nxt.d;
+                        const C zp = gradc<R, C>(p0, s, c, p1), zd = gradc<R, C>(d0, s, c, d1);
+                        v[0] += (double)(w * i2 * (zp.x * zp.x + zp.y * zp.y));
+                        v[C1] += (double)(w * i2 * (R)2.0 * (zp.x * zd.x + zp.y * zd.y));
+                        v[C2] += (double)(w * i2 * (zd.x * zd.x + zd.y * zd.y));
+                        if (NV == 17) {
+                            const R dph = d * (dir == 0 ? cur.da : cur.db);
+                            const R dph2 = dph * dph;
+                            // z = x0 * U(-ph) * conj(x1), U(-ph) = c + i s
+#define ZMUL(x0, x1, zr, zi)                                             \
+    {                                                                    \
+        R ur = x0.x * c - x0.y * s, ui = x0.x * s + x0.y * c;            \
+        zr = ur * x1.x + ui * x1.y;                                      \
+        zi = ui * x1.x - ur * x1.y;                                      \
+    }
+                            R zr, zi, z2r, z2i;
+                            ZMUL(p0, p1, zr, zi);
+                            v[1] += (double)(w * i2 * (R)2.0 * zi * dph);
+                            v[2] += (double)(w * i2 * zr * dph2);
+                            v[3] += (double)(-w * i2 / (R)3.0 * zi * dph2 * dph);
+                            v[4] += (double)(-w * i2 / (R)12.0 * zr * dph2 * dph2);
+                            ZMUL(p0, d1, zr, zi);
+                            ZMUL(d0, p1, z2r, z2i);
+                            zr += z2r; zi += z2i;
+                            v[6] += (double)(w * i2 * (R)2.0 * zi * dph);
+                            v[7] += (double)(w * i2 * zr * dph2);
+                            v[8] += (double)(-w * i2 / (R)3.0 * zi * dph2 * dph);
+                            v[9] += (double)(-w * i2 / (R)12.0 * zr * dph2 * dph2);
+                            ZMUL(d0, d1, zr, zi);
+                            v[11] += (double)(w * i2 * (R)2.0 * zi * dph);
+                            v[12] += (double)(w * i2 * zr * dph2);
+                            v[13] += (double)(-w * i2 / (R)3.0 * zi * dph2 * dph);
+                            v[14] += (double)(-w * i2 / (R)12.0 * zr * dph2 * dph2);
+#undef ZMUL
+                        }
+                    }
+                }
+                if (S.kappa2 > (R)0 && i < g.Nx - 1 && y < g.Ny - 1) {
+                    if (NV == 17) {
+                        R BH = -S.H;
+                        if (S.ae) BH += idx * (ebE - cur.eb) - idy * (nxt.ea - cur.ea);
+                        if (S.a) BH += idx * (bE - cur.b) - idy * (nxt.a - cur.a);
+                        const R dB = idx * (dbE - cur.db) - idy * (nxt.da - cur.da);
+                        v[0] += (double)(S.kappa2 * BH * BH);
+                        v[1] += (double)(S.kappa2 * (R)2.0 * BH * dB);
+                        v[2] += (double)(S.kappa2 * dB * dB);
+                    } else {
+                        const R dB = idx * (bE - cur.b) - idy * (nxt.a - cur.a) - S.H;
+                        v[0] += (double)(S.kappa2 * dB * dB);
+                    }
+                }
+                dpsi_new[n] = cur.d;
+                if (SOLVEA) { da_new[n] = cur.da; db_new[n] = cur.db; }
+            }
+            cur = nxt;
+        }
+    CGF_TILE_LOOP_END
+    block_sum_to_partials<NV>(v, partials, blockIdx.x);
+}
+
+// ============================================================================= Jacobians + PR sums
+template <typename R> struct RowG { typename V2<R>::type p; R sa, ca, sb, cb; };
+
+// curl-curl stencils with the boundary doubling of quirk Q10 (cg.h:176-217, 240-282): direct loads
+// (they hit L1: the rows were just read for the link phases)
+template <typename R>
+__device__ __forceinline__ R cgf_curl_a(const Geo &g, int j, size_t n, R H, const R *ae, const R *be, const R *a, const R *b) {
+    const R idy = (R)g.idy, idy2 = (R)g.idy2, idxy = (R)g.idxy;
+    const int P = g.P;
+    R v = 0, dd = 1;
+    if (j == 0) { v -= (R)2.0 * H * idy; dd = 2; }
+    else if (j + 1 == g.Ny) { v += (R)2.0 * H * idy; dd = 2; }
+    if (ae) v += (R)2.0 / dd * idy2 * ae[n];
+    if (a) v += (R)2.0 * idy2 * a[n];
+    if (j > 0) {
+        if (ae) v += (-idy2 * ae[n - P] + idxy * be[n - P] - idxy * be[n - P + 1]);
+        if (a) v += dd * (-idy2 * a[n - P] + idxy * b[n - P] - idxy * b[n - P + 1]);
+    }
+    if (j + 1 < g.Ny) {
+        if (ae) v += (-idy2 * ae[n + P] - idxy * be[n] + idxy * be[n + 1]);
+        if (a) v += dd * (-idy2 * a[n + P] - idxy * b[n] + idxy * b[n + 1]);
+    }
+    return v;
+}
+template <typename R>
+__device__ __forceinline__ R cgf_curl_b(const Geo &g, int i, size_t n, R H, const R *ae, const R *be, const R *a, const R *b) {
+    const R idx = (R)g.idx, idx2 = (R)g.idx2, idxy = (R)g.idxy;
+    const int P = g.P;
+    R v = 0, dd = 1;
+    if (i == 0) { v += (R)2.0 * H * idx; dd = 2; }
+    else if (i + 1 == g.Nx) { v -= (R)2.0 * H * idx; dd = 2; }
+    if (be) v += (R)2.0 / dd * idx2 * be[n];
+    if (b) v += (R)2.0 * idx2 * b[n];
+    if (i > 0) {
+        if (ae) v += (-idx2 * be[n - 1] + idxy * ae[n - 1] - idxy * ae[n - 1 + P]);
+        if (a) v += dd * (-idx2 * b[n - 1] + idxy * a[n - 1] - idxy * a[n - 1 + P]);
+    }
+    if (i + 1 < g.Nx) {
+        if (ae) v += (-idx2 * be[n + 1] - idxy * ae[n] + idxy * ae[n + P]);
+        if (a) v += dd * (-idx2 * b[n + 1] - idxy * a[n] + idxy * a[n + P]);
+    }
+    return v;
+}
+
+template <typename R, bool SOLVEA, bool PREV>
+__global__ void __launch_bounds__(CGF_THREADS, 2)
+k_cgf_grad(CgfState<R> S, typename V2<R>::type *__restrict__ gpsi, R *__restrict__ ga, R *__restrict__ gb,
+           const typename V2<R>::type *__restrict__ ppsi, const R *__restrict__ pa, const R *__restrict__ pb,
+           double *partials) {
+    typedef typename V2<R>::type C;
+    const Geo &g = S.g;
+    const R dx = (R)g.dx, dy = (R)g.dy, idx = (R)g.idx, idy = (R)g.idy, idx2 = (R)g.idx2, idy2 = (R)g.idy2;
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    // psi and the two link variables owned by node (ii, y): exp(-i dx A_a), exp(-i dy A_b) as (sin, cos)
+    auto load = [&](int ii, int y) {
+        RowG<R> r;
+        r.p.x = 0; r.p.y = 0; r.sa = 0; r.ca = 1; r.sb = 0; r.cb = 1;
+        if (ii >= 0 && ii < g.Nx && y >= 0) {
+            const size_t n = g.at(ii, y);
+            const unsigned f = S.nf[n];
+            r.p = S.psi[n];
+            if (f & (NF_PM | NF_PP)) {
+                R ph = 0;
+                if (S.ae) ph += S.ae[n];
+                if (S.a) ph += S.a[n];
+                sincos_r<R>(dx * ph, &r.sa, &r.ca);
+            }
+            if (f & (NF_MP | NF_PP)) {
+                R ph = 0;
+                if (S.be) ph += S.be[n];
+                if (S.b) ph += S.b[n];
+                sincos_r<R>(dy * ph, &r.sb, &r.cb);
+            }
+        }
+        return r;
+    };
+    CGF_TILE_LOOP_BEGIN
+        RowG<R> prv = load(i, ys - 1);
+        RowG<R> cur = load(i, ys);
+        for (int y = ys; y < ye; y++) {
+            const RowG<R> nxt = load(i, y + 1);
+            C pE = shfl_down_c<C>(cur.p), pW = shfl_up_c<C>(cur.p);
+            R sW = __shfl_up_sync(FULL, cur.sa, 1), cW = __shfl_up_sync(FULL, cur.ca, 1);
+            if (lane == 31) { if (i + 1 < g.Nx) pE = S.psi[g.at(i + 1, y)]; else { pE.x = 0; pE.y = 0; } }
+            if (lane == 0) { const RowG<R> w = load(i - 1, y); pW = w.p; sW = w.sa; cW = w.ca; }
+            if (in) {
+                const size_t n = g.at(i, y);
+                const unsigned f = S.nf[n];
+                const R eps = S.epsf ? S.epsf[n] : S.eps;
+                const C p0 = cur.p;
+                C gj;
+                gj.x = 0; gj.y = 0;
+                if (f) {
+                    R wW, wE, wS, wN, gw;
+                    du_w<R>(f, wW, wE, wS, wN, gw);
+                    const R p = p0.x * p0.x + p0.y * p0.y - eps;
+                    gj.x += (R)2.0 * gw * p * p0.x;
+                    gj.y += (R)2.0 * gw * p * p0.y;
+                    // g_grad_jac_psi(psi0, ph, psi1) = 2 (psi0 - psi1 U(ph))  (cg.h:5-12); the W and S links
+                    // enter with the opposite phase: sincos(-x) = (-sin x, cos x)
+                    if (f & (NF_MM | NF_MP)) {
+                        const C z = gradc<R, C>(p0, -sW, cW, pW);
+                        gj.x += wW * idx2 * ((R)-2.0 * z.x); gj.y += wW * idx2 * ((R)-2.0 * z.y);
+                    }
+                    if (f & (NF_PM | NF_PP)) {
+                        const C z = gradc<R, C>(p0, cur.sa, cur.ca, pE);
+                        gj.x += wE * idx2 * ((R)-2.0 * z.x); gj.y += wE * idx2 * ((R)-2.0 * z.y);
+                    }
+                    if (f & (NF_MM | NF_PM)) {
+                        const C z = gradc<R, C>(p0, -prv.sb, prv.cb, prv.p);
+                        gj.x += wS * idy2 * ((R)-2.0 * z.x); gj.y += wS * idy2 * ((R)-2.0 * z.y);
+                    }
+                    if (f & (NF_MP | NF_PP)) {
+                        const C z = gradc<R, C>(p0, cur.sb, cur.cb, nxt.p);
+                        gj.x += wN * idy2 * ((R)-2.0 * z.x); gj.y += wN * idy2 * ((R)-2.0 * z.y);
+                    }
+                }
+                const R dxdy = dx * dy;
+                gj.x *= dxdy; gj.y *= dxdy;
+                gpsi[n] = gj;
+                if (PREV) {
+                    const C q = ppsi[n];
+                    v[0] += (double)(gj.x * (gj.x - q.x) + gj.y * (gj.y - q.y));
+                    v[1] += (double)(q.x * q.x + q.y * q.y);
+                }
+                if (SOLVEA) {
+                    const R pm = (f & NF_PM) ? (R)1 : (R)0, pp = (f & NF_PP) ? (R)1 : (R)0, mp = (f & NF_MP) ? (R)1 : (R)0;
+                    if (i < g.Nx - 1) {
+                        R w = S.kappa2 * cgf_curl_a<R>(g, y, n, S.H, S.ae, S.be, S.a, S.b);
+                        if (f & (NF_PM | NF_PP)) {
+                            const R js = (p0.x * pE.y - p0.y * pE.x) * cur.ca - (p0.x * pE.x + p0.y * pE.y) * cur.sa;
+                            w += -((R)0.5 * (pm + pp)) * idx * js;
+                        }
+                        w = (R)2.0 * dx * dy * w;
+                        ga[n] = w;
+                        if (PREV) { const R q = pa[n]; v[2] += (double)(w * (w - q)); v[3] += (double)(q * q); }
+                    }
+                    if (y < g.Ny - 1) {
+                        R w = S.kappa2 * cgf_curl_b<R>(g, i, n, S.H, S.ae, S.be, S.a, S.b);
+                        if (f & (NF_MP | NF_PP)) {
+                            const R js = (p0.x * nxt.p.y - p0.y * nxt.p.x) * cur.cb - (p0.x * nxt.p.x + p0.y * nxt.p.y) * cur.sb;
+                            w += -((R)0.5 * (mp + pp)) * idy * js;
+                        }
+                        w = (R)2.0 * dx * dy * w;
+                        gb[n] = w;
+                        if (PREV) { const R q = pb[n]; v[2] += (double)(w * (w - q)); v[3] += (double)(q * q); }
+                    }
+                }
+            }
+            prv = cur;
+            cur = nxt;
+        }
+    CGF_TILE_LOOP_END
+    if (PREV) block_sum_to_partials<4>(v, partials, blockIdx.x);
+}
+
+// beta = max(num/den, 0) in real_t, nan -> 0 (divide_scalars_positive, utils.h:140-146); stays on the device
+template <typename R>
+__global__ void k_cgf_beta(const double *__restrict__ sums, double *beta) {
+    if (threadIdx.x < 2) {
+        R q = (R)sums[2 * threadIdx.x] / (R)sums[2 * threadIdx.x + 1];
+        beta[threadIdx.x] = (q > (R)0) ? (double)q : 0.0;
+    }
+}
+
+// ----------------------------------------------------------------------------- host side
+static int cgf_grid(svl_ctx *c) {
+    const Geo &g = c->g;
+    int ntiles = ((g.Nx + 31) / 32) * ((g.j1 - g.j0 + CGF_WARPS * CGF_V - 1) / (CGF_WARPS * CGF_V));
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+    int cap = nsm * 2 * 4;                       // a few waves of resident CTAs: balances the tail, ~1200 partials
+    return ntiles < cap ? ntiles : cap;
+}
+
+template <typename R>
+static CgfState<R> cgf_state(svl_ctx *c, double kappa2, double eps, const svl_buf *epsf, double H, const svl_buf *psi,
+                             const svl_buf *abei, const svl_buf *ab) {
+    typedef typename V2<R>::type C;
+    CgfState<R> S;
+    S.g = c->g;
+    S.kappa2 = (R)kappa2; S.eps = (R)eps; S.H = (R)H;
+    S.epsf = epsf ? (const R *)epsf->p[0] : nullptr;
+    S.nf = c->nf;
+    S.psi = (const C *)psi->p[0];
+    S.ae = abei ? (const R *)abei->p[0] : nullptr; S.be = abei ? (const R *)abei->p[1] : nullptr;
+    S.a = ab ? (const R *)ab->p[0] : nullptr; S.b = ab ? (const R *)ab->p[1] : nullptr;
+    return S;
+}
+
+template <typename R>
+static int cgf_begin_t(svl_ctx *c, int solveA, int have_prev, double kappa2, double eps, const svl_buf *epsf, double H,
+                       const svl_buf *psi, const svl_buf *abei, const svl_buf *ab, svl_buf *g_psi, svl_buf *g_psi_prev,
+                       svl_buf *d_psi, svl_buf *g_A, svl_buf *g_A_prev, svl_buf *d_A, double *beta, double *c_out) {
+    typedef typename V2<R>::type C;
+    const int nb = cgf_grid(c);
+    SVL_TRY(svl_ensure_partials(c, (size_t)nb * 17));
+    CgfState<R> S = cgf_state<R>(c, kappa2, eps, epsf, H, psi, abei, ab);
+    R *gA0 = solveA ? (R *)g_A->p[0] : nullptr, *gA1 = solveA ? (R *)g_A->p[1] : nullptr;
+    const R *pA0 = solveA ? (const R *)g_A_prev->p[0] : nullptr, *pA1 = solveA ? (const R *)g_A_prev->p[1] : nullptr;
+#define GRAD_ARGS S, (C *)g_psi->p[0], gA0, gA1, (const C *)g_psi_prev->p[0], pA0, pA1, c->partials
+    if (solveA && have_prev) k_cgf_grad<R, true, true><<<nb, CGF_THREADS, 0, c->stream>>>(GRAD_ARGS);
+    else if (solveA) k_cgf_grad<R, true, false><<<nb, CGF_THREADS, 0, c->stream>>>(GRAD_ARGS);
+    else if (have_prev) k_cgf_grad<R, false, true><<<nb, CGF_THREADS, 0, c->stream>>>(GRAD_ARGS);
+    else k_cgf_grad<R, false, false><<<nb, CGF_THREADS, 0, c->stream>>>(GRAD_ARGS);
+#undef GRAD_ARGS
+    SVL_CHECK(cudaGetLastError());
+    c->stat_launches += 1;
+    double *dbeta = c->d_result + 32;                 // device-resident beta[2]
+    if (have_prev) {
+        SVL_TRY(svl_finish_sum(c, nb, 4, 1.0, nullptr));          // d_result[0..3], no host read
+        k_cgf_beta<R><<<1, 32, 0, c->stream>>>(c->d_result, dbeta);
+        SVL_CHECK(cudaGetLastError());
+        c->stat_launches += 1;
+    } else {
+        // first iteration of a cg() call: keep the betas of the previous call (quirk Q6)
+        c->h_result[40] = beta[0]; c->h_result[41] = beta[1];
+        SVL_CHECK(cudaMemcpyAsync(dbeta, c->h_result + 40, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    // direction update fused with the coefficients; new directions go to scratch planes, then swap
+    svl_buf *dn_psi = nullptr, *dn_A = nullptr;
+    SVL_TRY(svl_scratch_node(c, 0, &dn_psi));
+    if (solveA) SVL_TRY(svl_scratch_edge(c, 0, &dn_A));
+    // Quirk Q11: the coefficient kernels use the scalar eps (0.0 when eps is a field)
+    S.eps = (R)(epsf ? 0.0 : eps);
+    if (solveA) {
+        k_cgf_coef<R, 17><<<nb, CGF_THREADS, 0, c->stream>>>(S, dbeta, (const C *)g_psi->p[0], gA0, gA1,
+                                                           (const C *)d_psi->p[0], (const R *)d_A->p[0],
+                                                           (const R *)d_A->p[1], (C *)dn_psi->p[0], (R *)dn_A->p[0],
+                                                           (R *)dn_A->p[1], c->partials);
+    } else {
+        k_cgf_coef<R, 5><<<nb, CGF_THREADS, 0, c->stream>>>(S, dbeta, (const C *)g_psi->p[0], nullptr, nullptr,
+                                                          (const C *)d_psi->p[0], nullptr, nullptr, (C *)dn_psi->p[0],
+                                                          nullptr, nullptr, c->partials);
+    }
+    SVL_CHECK(cudaGetLastError());
+    c->stat_launches += 1;
+    SVL_TRY(svl_swap(c, d_psi, dn_psi));
+    if (solveA) SVL_TRY(svl_swap(c, d_A, dn_A));
+    SVL_CHECK(cudaMemcpyAsync(c->h_result + 32, dbeta, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SVL_TRY(svl_finish_sum(c, nb, solveA ? 17 : 5, (double)((R)c->g.dx * (R)c->g.dy), c_out));   // one host sync
+    beta[0] = c->h_result[32];
+    if (solveA) beta[1] = c->h_result[33];
+    return 0;
+}
+
+template <typename R>
+static int cgf_end_t(svl_ctx *c, int solveA, double kappa2, double eps, const svl_buf *epsf, double H, svl_buf *psi,
+                     const svl_buf *abei, svl_buf *ab, const svl_buf *d_psi, const svl_buf *d_A, double alpha_psi,
+                     double alpha_A, double *E_out) {
+    typedef typename V2<R>::type C;
+    const int nb = cgf_grid(c);
+    SVL_TRY(svl_ensure_partials(c, (size_t)nb));
+    CgfState<R> S = cgf_state<R>(c, kappa2, eps, epsf, H, psi, abei, ab);
+    svl_buf *pn = nullptr, *An = nullptr;
+    SVL_TRY(svl_scratch_node(c, 0, &pn));
+    if (solveA) SVL_TRY(svl_scratch_edge(c, 0, &An));
+    if (solveA)
+        k_cgf_update<R, true><<<nb, CGF_THREADS, 0, c->stream>>>(S, (const C *)d_psi->p[0], (const R *)d_A->p[0],
+                                                                (const R *)d_A->p[1], (R)alpha_psi, (R)alpha_A,
+                                                                (C *)pn->p[0], (R *)An->p[0], (R *)An->p[1], c->partials);
+    else
+        k_cgf_update<R, false><<<nb, CGF_THREADS, 0, c->stream>>>(S, (const C *)d_psi->p[0], nullptr, nullptr,
+                                                                 (R)alpha_psi, (R)0, (C *)pn->p[0], nullptr, nullptr,
+                                                                 c->partials);
+    SVL_CHECK(cudaGetLastError());
+    c->stat_launches += 1;
+    SVL_TRY(svl_swap(c, psi, pn));
+    if (solveA) SVL_TRY(svl_swap(c, ab, An));
+    double E = 0.0;
+    SVL_TRY(svl_finish_sum(c, nb, 1, (double)((R)c->g.dx * (R)c->g.dy), &E));
+    if (E_out) *E_out = E;
+    return 0;
+}
+
+int svl_cgf_begin(svl_ctx *c, int solveA, int have_prev, double kappa2, double eps, const svl_buf *epsf, double H,
+                  const svl_buf *psi, const svl_buf *abei, const svl_buf *ab, svl_buf *g_psi, svl_buf *g_psi_prev,
+                  svl_buf *d_psi, svl_buf *g_A, svl_buf *g_A_prev, svl_buf *d_A, double *beta, double *c_out) {
+    if (c->rsize == 4) return cgf_begin_t<float>(c, solveA, have_prev, kappa2, eps, epsf, H, psi, abei, ab, g_psi, g_psi_prev,
+                                                 d_psi, g_A, g_A_prev, d_A, beta, c_out);
+    return cgf_begin_t<double>(c, solveA, have_prev, kappa2, eps, epsf, H, psi, abei, ab, g_psi, g_psi_prev, d_psi, g_A,
+                               g_A_prev, d_A, beta, c_out);
+}
+
+int svl_cgf_end(svl_ctx *c, int solveA, double kappa2, double eps, const svl_buf *epsf, double H, svl_buf *psi,
+                const svl_buf *abei, svl_buf *ab, const svl_buf *d_psi, const svl_buf *d_A, double alpha_psi,
+                double alpha_A, double *E_out) {
+    if (c->rsize == 4) return cgf_end_t<float>(c, solveA, kappa2, eps, epsf, H, psi, abei, ab, d_psi, d_A, alpha_psi, alpha_A, E_out);
+    return cgf_end_t<double>(c, solveA, kappa2, eps, epsf, H, psi, abei, ab, d_psi, d_A, alpha_psi, alpha_A, E_out);
+}

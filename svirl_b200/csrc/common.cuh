@@ -92,7 +92,7 @@ struct svl_ctx {
     // vortex candidates
     long long *d_cand; double *d_candv; unsigned long long *d_ncand; size_t cand_cap;
     // options / stats
-    int opt_psi_kernel, opt_psi_k, opt_tma, opt_graphs, opt_a_kernel;
+    int opt_psi_kernel, opt_psi_k, opt_tma, opt_graphs, opt_a_kernel, opt_cg_fused;
     int pred_psi, pred_A;          // sweep counts of the previous solve
     int pred_psi2, pred_A2;        // ... and of the one before (trend)
     double stat_launches, stat_replays, stat_psi_sweeps, stat_A_sweeps;
@@ -145,8 +145,7 @@ template <typename R> __device__ __forceinline__ void sincos_r(R x, R *s, R *c);
 // a third of its instructions).  Larger arguments take libdevice's sincosf.
 struct sc_f { float s, c; };
 static __device__ __noinline__ sc_f sincosf_slow(float x) { sc_f r; sincosf(x, &r.s, &r.c); return r; }
-template <> __device__ __forceinline__ void sincos_r<float>(float x, float *s, float *c) {
-    if (fabsf(x) > 20000.0f) { sc_f r = sincosf_slow(x); *s = r.s; *c = r.c; return; }   // out of line, by value
+__device__ __forceinline__ void sincos_fast32(float x, float *s, float *c) {
     float j = rintf(x * 0.636619772f);
     int q = __float2int_rn(j);
     float r = fmaf(j, -1.5707962513e+0f, x);
@@ -161,7 +160,62 @@ template <> __device__ __forceinline__ void sincos_r<float>(float x, float *s, f
     *s = (q & 2) ? -s2 : s2;
     *c = ((q + 1) & 2) ? -c2 : c2;
 }
-template <> __device__ __forceinline__ void sincos_r<double>(double x, double *s, double *c) { sincos(x, s, c); }
+template <> __device__ __forceinline__ void sincos_r<float>(float x, float *s, float *c) {
+    if (fabsf(x) > 20000.0f) { sc_f r = sincosf_slow(x); *s = r.s; *c = r.c; return; }   // out of line, by value
+    sincos_fast32(x, s, c);
+}
+// fp64: libdevice's sincos() rounds the quadrant with F2I/I2F conversions, which run on the XU
+// pipe at a small fraction of the FP64 rate -- ncu showed that pipe saturated (150 % "realtime")
+// in every kernel that evaluates link variables.  This version stays on the FP64 pipe: quadrant
+// by the 1.5*2^52 magic-number rounding, 3-term Cody-Waite reduction of pi/2 with FMAs (good for
+// |x| < 1e5), fdlibm's degree-13/-12 minimax kernels on [-pi/4, pi/4] (public-domain coefficients).
+// Max error ~1 ulp (checked against libdevice in tests/test_gpu_parity.py::test_sincos_accuracy).
+struct sc_d { double s, c; };
+static __device__ __noinline__ sc_d sincos_slow(double x) { sc_d r; sincos(x, &r.s, &r.c); return r; }
+__constant__ double SVL_SC[16] = {
+    // pi/2 split in three doubles; 2/pi
+    1.5707963267948966e+00, 6.1232339957367574e-17, 8.4784276603688985e-32, 6.3661977236758138e-01,
+    // sin: r + r z (S1 + z (S2 + ... z S6))
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+    2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+    // cos: 1 - z/2 + z z (C1 + z (C2 + ... z C6))
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+    -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
+// branch-free core, valid for |x| <= SVL_SC_LIMIT; callers that evaluate many link variables test
+// the range once for all of them (sincos_many_ok) so that the polynomials of different links
+// interleave (instruction-level parallelism instead of one dependent Horner chain at a time).
+#define SVL_SC_LIMIT 1.0e5
+__device__ __forceinline__ void sincos_fast(double x, double *s, double *c) {
+    const double MAGIC = 6755399441055744.0;               // 1.5 * 2^52: rint() in the low mantissa bits
+    double t = fma(x, SVL_SC[3], MAGIC);
+    int q = __double2loint(t);
+    double j = t - MAGIC;
+    double r = fma(j, -SVL_SC[0], x);
+    r = fma(j, -SVL_SC[1], r);
+    r = fma(j, -SVL_SC[2], r);
+    double z = r * r;
+    double ps = fma(SVL_SC[9], z, SVL_SC[8]);
+    ps = fma(ps, z, SVL_SC[7]); ps = fma(ps, z, SVL_SC[6]); ps = fma(ps, z, SVL_SC[5]); ps = fma(ps, z, SVL_SC[4]);
+    double sn = fma(ps * z, r, r);
+    double pc = fma(SVL_SC[15], z, SVL_SC[14]);
+    pc = fma(pc, z, SVL_SC[13]); pc = fma(pc, z, SVL_SC[12]); pc = fma(pc, z, SVL_SC[11]); pc = fma(pc, z, SVL_SC[10]);
+    double cs = fma(pc * z, z, fma(-0.5, z, 1.0));
+    // quadrant: swap for odd q, flip signs through the high word (bit 1 of q / q+1 -> bit 31)
+    double s2 = (q & 1) ? cs : sn, c2 = (q & 1) ? sn : cs;
+    int hs = __double2hiint(s2) ^ ((q << 30) & 0x80000000), hc = __double2hiint(c2) ^ (((q + 1) << 30) & 0x80000000);
+    *s = __hiloint2double(hs, __double2loint(s2));
+    *c = __hiloint2double(hc, __double2loint(c2));
+}
+__device__ __forceinline__ void sincos_fast(float x, float *s, float *c) { sincos_fast32(x, s, c); }
+__device__ __forceinline__ bool sincos_fast_ok(double x) { return fabs(x) <= SVL_SC_LIMIT; }
+__device__ __forceinline__ bool sincos_fast_ok(float x) { return fabsf(x) <= 20000.0f; }
+// out-of-line libdevice evaluation (any argument): the rare path of callers that test the range themselves
+__device__ __forceinline__ void sincos_any(double x, double *s, double *c) { sc_d r = sincos_slow(x); *s = r.s; *c = r.c; }
+__device__ __forceinline__ void sincos_any(float x, float *s, float *c) { sc_f r = sincosf_slow(x); *s = r.s; *c = r.c; }
+template <> __device__ __forceinline__ void sincos_r<double>(double x, double *s, double *c) {
+    if (fabs(x) > SVL_SC_LIMIT) { sc_d r = sincos_slow(x); *s = r.s; *c = r.c; return; }
+    sincos_fast(x, s, c);
+}
 // 1/x for x of order 1 (the Jacobi diagonal): MUFU.RCP + one Newton step, ~1 ulp, no slow path
 __device__ __forceinline__ float rcp_r(float x) {
     float r;

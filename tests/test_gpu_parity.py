@@ -306,3 +306,68 @@ def test_a_tile_kernel_equals_plain_kernel_large_grid(dtype, lang):
         assert out[0][3] == out[1][3]
     for k in range(3):
         assert np.abs(out[0][k] - out[1][k]).max() < tol
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_sincos_accuracy(dtype):
+    """The library's own sincos (every link variable exp(-i d A) goes through it) against the host
+    libm in extended precision: <= 2 ulp over the argument range the fast path covers, and exact
+    hand-over to the slow path beyond it."""
+    import ctypes as C
+    from svirl_b200 import GLSolver, _lib
+    gl = GLSolver(Nx=16, Ny=16, dx=0.5, dy=0.5, dtype=dtype)
+    rs = np.random.RandomState(9)
+    lim = 1.0e5 if dtype is np.float64 else 2.0e4
+    x = np.concatenate([rs.uniform(-4, 4, 200000), rs.uniform(-300, 300, 200000), rs.uniform(-lim, lim, 200000),
+                        np.arange(-64, 65) * (np.pi / 4), [0.0, 1e-300, -1e-9, 3 * lim, -7 * lim, 1e9]])
+    x = x.astype(dtype).astype(np.float64)
+    s, c = np.empty_like(x), np.empty_like(x)
+    pd = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    _lib.call("svl_debug_sincos", gl.par.ctx, x.size, pd(x), pd(s), pd(c))
+    xl = x.astype(np.longdouble)
+    es, ec = np.abs(s - np.sin(xl)).astype(np.float64), np.abs(c - np.cos(xl)).astype(np.float64)
+    ulp = np.finfo(dtype).eps            # results are in [-1, 1]: absolute error in units of eps
+    assert es.max() < 2.0 * ulp and ec.max() < 2.0 * ulp, (es.max() / ulp, ec.max() / ulp)
+
+
+@pytest.mark.parametrize("case", ["f64_k2_holes_epsfield_ext", "f64_kinf_holes", "f32_k2_holes", "f32_kinf"])
+def test_cg_fused_iteration_equals_kernel_composition(case):
+    """The three-pass CG iteration (cg_fused.cu: Jacobians+PR sums / direction+coefficients /
+    update+energy) against the composition of the single kernels (option cg_fused=0, the kernels
+    checked one by one against the reference in test_kernels) on a multi-tile 300 x 270 grid:
+    same energies and same state to rounding, including a second cg() call (quirk Q6)."""
+    from svirl_b200 import GLSolver
+    dtype = np.float64 if case.startswith("f64") else np.float32
+    Nx, Ny = 300, 270
+    rs = np.random.RandomState(11)
+    mt = rs.rand(Nx - 1, Ny - 1) > 0.1
+    kw = dict(Nx=Nx, Ny=Ny, dx=0.5, dy=0.4, dtype=dtype, homogeneous_external_field=0.1, random_seed=7,
+              gl_parameter=np.inf if "kinf" in case else 2.0, normal_conductivity=10.0)
+    if "holes" in case:
+        kw["material_tiling"] = mt
+    if "epsfield" in case:
+        kw["linear_coefficient"] = (0.7 + 0.3 * rs.rand(Nx, Ny)).astype(dtype)
+    res = []
+    for fused in (0, 1):
+        gl = GLSolver(**kw)
+        if "ext" in case:
+            r2 = np.random.RandomState(3)
+            gl.params.external_vector_potential = (0.05 * r2.rand(Nx - 1, Ny).astype(dtype), 0.05 * r2.rand(Nx, Ny - 1).astype(dtype))
+        gl.par.set_option("cg_fused", fused)
+        gl.solve.td(dt=0.1, Nt=5)
+        gl.solve.cg(n_iter=4)
+        E1 = np.array(gl.solve._cg.cg_energies, dtype=np.float64)
+        gl.solve.cg(n_iter=3)
+        E2 = np.array(gl.solve._cg.cg_energies, dtype=np.float64)
+        a, b = gl.vars.vector_potential
+        res.append((E1, E2, gl.vars.order_parameter, a, b))
+        gl.par.close()
+    f64 = dtype is np.float64
+    # finite kappa goes through SciPy BFGS, which amplifies rounding differences of the coefficients
+    # (the energies are sums with heavy cancellation: compare on the scale of the first one)
+    rt = (1e-8 if "kinf" not in case else 1e-12) if f64 else 2e-4
+    at = rt * np.abs(res[0][0]).max()
+    assert np.allclose(res[0][0], res[1][0], rtol=rt, atol=at) and np.allclose(res[0][1], res[1][1], rtol=rt, atol=at)
+    tol = (1e-7 if "kinf" not in case else 1e-11) if f64 else 2e-3
+    for k in (2, 3, 4):
+        assert np.abs(res[0][k] - res[1][k]).max() < tol
