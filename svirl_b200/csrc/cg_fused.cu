@@ -10,9 +10,9 @@
 //                 state (utils.h:74-92, observables.h:251-362)
 //
 // All three walk the grid the same way: a warp owns 32 consecutive columns and a strip of V rows;
-// the lanes hold one node each, the E/W neighbours come from warp shuffles (the two edge lanes load
-// theirs), the N neighbour is the next row of the strip (one row of look-ahead), the S neighbour the
-// previous one.  Every link variable exp(-i d A) is evaluated once by the node that owns the edge
+// the lanes hold one node each, the E/W neighbours come from warp shuffles (adjacent warps overlap by
+// one or two columns so that no lane loads a neighbour by itself), the N neighbour is the next row
+// of the strip, the S neighbour the previous one; rows are loaded two ahead of their use.  Every link variable exp(-i d A) is evaluated once by the node that owns the edge
 // (2 sincos per node instead of 6 in the Jacobians) and never stored.  CTAs are persistent
 // (tile = 32 columns x 8V rows, tiles dealt round-robin), reductions accumulate in double in
 // registers across all tiles of a CTA and are reduced once per CTA in a fixed order, so the sums are
@@ -21,13 +21,13 @@
 // caller swaps storage.
 #include "common.cuh"
 
-#define CGF_V 8
 #define CGF_WARPS 8
 #define CGF_THREADS (32 * CGF_WARPS)
 #define FULL 0xffffffffu
 
 template <typename R> struct CgfState {     // what all three kernels read
     Geo g;
+    int V;                                  // rows per strip (run time: 32 on large grids, fewer on small ones)
     R kappa2, eps, H;
     const R *epsf;
     const uint8_t *nf;
@@ -62,58 +62,105 @@ template <typename R, typename C> __device__ __forceinline__ C gradc(C p0, R s, 
     return z;
 }
 
-// tile walk shared by the three kernels
-#define CGF_TILE_LOOP_BEGIN                                                                        \
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;                                    \
-    const int ntx = (g.Nx + 31) / 32, RT = CGF_WARPS * CGF_V;                                      \
-    const int nty = (g.j1 - g.j0 + RT - 1) / RT;                                                   \
+// One lane asks the L2 for a whole row segment (cp.async.bulk.prefetch: no registers, no scoreboard):
+// at the start of a strip the lanes 0..V-1 request rows ys+2..ye of every plane the kernel reads, so
+// the register loads two rows ahead hit L2 (~250 cycles) instead of HBM (~1000 under load).
+__device__ __forceinline__ void cgf_pf(const void *base, size_t elem, int nelem, int esize) {
+    if (!base) return;
+    const size_t b0 = elem * (size_t)esize, a0 = b0 & ~(size_t)15;
+    const uint32_t nb = (uint32_t)(((b0 + (size_t)nelem * esize + 15) & ~(size_t)15) - a0);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char *)base + a0), "r"(nb) : "memory");
+}
+
+// Tile walk shared by the three kernels: the 8 warps of a CTA sit side by side along x (a CTA row is
+// one contiguous 2-4 KB run per plane: DRAM pages stay open) and walk the same V rows.  A warp reads
+// 32 consecutive columns but produces only WOUT
+// of them (lanes LPAD .. LPAD+WOUT-1): the remaining lane(s) exist to hand their values to the
+// neighbours by shuffle, so no lane ever has to load a neighbour column on its own (a divergent,
+// fully exposed memory latency per row otherwise).  Rows are loaded two ahead of the one being
+// computed, so the loads of row y+2 are in flight while row y is evaluated.
+#define CGF_TILE_LOOP_BEGIN(WOUT, LPAD)                                                            \
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;           \
+    const int ntx = (g.Nx + (WOUT) * nwarp - 1) / ((WOUT) * nwarp);                                \
+    const int nty = (g.j1 - g.j0 + S.V - 1) / S.V;                                                 \
     for (int t = blockIdx.x; t < ntx * nty; t += gridDim.x) {                                      \
-        const int i = (t % ntx) * 32 + lane;                                                       \
-        const int ys = g.j0 + (t / ntx) * RT + warp * CGF_V;                                       \
-        if (ys >= g.j1) continue;                                                                  \
-        const int ye = ys + CGF_V < g.j1 ? ys + CGF_V : g.j1;                                      \
-        const bool in = i < g.Nx;
+        const int i = ((t % ntx) * nwarp + warp) * (WOUT) + lane - (LPAD);                         \
+        const int ys = g.j0 + (t / ntx) * S.V;                                                     \
+        const int ye = ys + S.V < g.j1 ? ys + S.V : g.j1;                                          \
+        if (i - lane + (LPAD) >= g.Nx) continue;                                                   \
+        const bool in = lane >= (LPAD) && lane < (LPAD) + (WOUT) && i < g.Nx;
 #define CGF_TILE_LOOP_END }
+// inside the tile loop: lane l requests row ys+2+l (<= ye; V <= 32) of the listed planes, columns of this warp
+#define CGF_PF_BEGIN                                                                               \
+    {                                                                                              \
+        const int pfy = ys + 2 + lane;                                                             \
+        const int pi0 = (i - lane) < 0 ? 0 : (i - lane);                                           \
+        const int pn_ = (pi0 + 33 <= g.Nx ? pi0 + 33 : g.Nx) - pi0;                                \
+        if (pfy <= ye && pn_ > 0) {                                                \
+            const size_t pe = g.at(pi0, pfy);
+#define CGF_PF(ptr, esize) cgf_pf((const void *)(ptr), pe, pn_, (int)(esize));
+#define CGF_PF_END }}
 
 // ============================================================================= update + energy
-template <typename R> struct RowU { typename V2<R>::type p; R a, b, ea, eb; };
+template <typename R> struct RawU { typename V2<R>::type p, d; R a, b, da, db, ea, eb, eps; unsigned f; };
+template <typename R> struct RowU { typename V2<R>::type p; R a, b, ea, eb, eps; unsigned f; };
 
-template <typename R, bool SOLVEA>
+template <typename R, bool SOLVEA, bool EXT>
 __global__ void __launch_bounds__(CGF_THREADS, 2)
 k_cgf_update(CgfState<R> S, const typename V2<R>::type *__restrict__ dpsi, const R *__restrict__ da,
              const R *__restrict__ db, R alpha_psi, R alpha_A, typename V2<R>::type *__restrict__ psi_out,
              R *__restrict__ a_out, R *__restrict__ b_out, double *partials) {
     typedef typename V2<R>::type C;
     const Geo &g = S.g;
+    const R *const ae_ = EXT ? S.ae : nullptr, *const be_ = EXT ? S.be : nullptr;   // compile-time absent without an external potential
     const R dx = (R)g.dx, dy = (R)g.dy, idx = (R)g.idx, idy = (R)g.idy, idx2 = (R)g.idx2, idy2 = (R)g.idy2;
     double acc[1] = {0.0};
-    // updated state of node (ii, y); zero outside the grid (rows are always inside the plane)
-    auto load = [&](int ii, int y) {
-        RowU<R> r;
-        r.p.x = 0; r.p.y = 0; r.a = 0; r.b = 0; r.ea = 0; r.eb = 0;
-        if (ii < g.Nx) {
+    // Raw row data (plain loads, no arithmetic: the loads stay in flight until the row is combined two
+    // iterations later) and the updated state of a node; zero outside the grid (rows are always
+    // inside the plane).
+    auto loadraw = [&](int ii, int y) {
+        RawU<R> r;
+        r.p.x = 0; r.p.y = 0; r.d.x = 0; r.d.y = 0; r.a = 0; r.b = 0; r.da = 0; r.db = 0; r.ea = 0; r.eb = 0;
+        r.eps = S.eps; r.f = 0;
+        if (ii >= 0 && ii < g.Nx) {
             const size_t n = g.at(ii, y);
-            const C p = S.psi[n], d = dpsi[n];
-            r.p.x = alpha_psi * d.x + p.x; r.p.y = alpha_psi * d.y + p.y;
+            r.p = S.psi[n]; r.d = dpsi[n];
+            r.f = S.nf[n];
+            if (S.epsf) r.eps = S.epsf[n];
             if (S.a) {
                 r.a = S.a[n]; r.b = S.b[n];
-                if (SOLVEA) { r.a = alpha_A * da[n] + r.a; r.b = alpha_A * db[n] + r.b; }
+                if (SOLVEA) { r.da = da[n]; r.db = db[n]; }
             }
-            if (S.ae) { r.ea = S.ae[n]; r.eb = S.be[n]; }
+            if (ae_) { r.ea = ae_[n]; r.eb = be_[n]; }
         }
         return r;
     };
-    CGF_TILE_LOOP_BEGIN
-        RowU<R> cur = load(i, ys);
+    auto combine = [&](const RawU<R> &w) {
+        RowU<R> r;
+        r.p.x = alpha_psi * w.d.x + w.p.x; r.p.y = alpha_psi * w.d.y + w.p.y;      // axpy_c (utils.h:74-82)
+        r.a = w.a; r.b = w.b;
+        if (SOLVEA) { r.a = alpha_A * w.da + w.a; r.b = alpha_A * w.db + w.b; }
+        r.ea = w.ea; r.eb = w.eb; r.eps = w.eps; r.f = w.f;
+        return r;
+    };
+    CGF_TILE_LOOP_BEGIN(31, 0)
+        CGF_PF_BEGIN
+            CGF_PF(S.psi, sizeof(C)) CGF_PF(dpsi, sizeof(C)) CGF_PF(S.a, sizeof(R)) CGF_PF(S.b, sizeof(R))
+            CGF_PF(da, sizeof(R)) CGF_PF(db, sizeof(R)) CGF_PF(ae_, sizeof(R)) CGF_PF(be_, sizeof(R))
+            CGF_PF(S.epsf, sizeof(R)) CGF_PF(S.nf, 1)
+        CGF_PF_END
+        RowU<R> cur = combine(loadraw(i, ys));
+        RawU<R> rawn = loadraw(i, ys + 1), raw2 = loadraw(ys + 2 <= ye ? i : -1, ys + 2);
         for (int y = ys; y < ye; y++) {
-            const RowU<R> nxt = load(i, y + 1);
-            C pE = shfl_down_c<C>(cur.p);
-            R bE = __shfl_down_sync(FULL, cur.b, 1), ebE = __shfl_down_sync(FULL, cur.eb, 1);
-            if (lane == 31) { const RowU<R> e = load(i + 1, y); pE = e.p; bE = e.b; ebE = e.eb; }
+            const RowU<R> nxt = combine(rawn);
+            rawn = raw2;
+            raw2 = loadraw(y + 3 <= ye ? i : -1, y + 3);
+            const C pE = shfl_down_c<C>(cur.p);
+            const R bE = __shfl_down_sync(FULL, cur.b, 1), ebE = __shfl_down_sync(FULL, cur.eb, 1);
             if (in) {
                 const size_t n = g.at(i, y);
-                const unsigned f = S.nf[n];
-                const R eps = S.epsf ? S.epsf[n] : S.eps;
+                const unsigned f = cur.f;
+                const R eps = cur.eps;
                 R e = 0;
                 if (f) {
                     R wW, wE, wS, wN, gw;
@@ -122,19 +169,19 @@ k_cgf_update(CgfState<R> S, const typename V2<R>::type *__restrict__ dpsi, const
                     e += gw * ((R)0.5 * p2 - eps) * p2;
                     R s, c;
                     if (f & (NF_PM | NF_PP)) {
-                        sincos_r<R>(dx * (S.ae ? cur.ea + cur.a : cur.a), &s, &c);
+                        sincos_r<R>(dx * (ae_ ? cur.ea + cur.a : cur.a), &s, &c);
                         const C z = gradc<R, C>(cur.p, s, c, pE);
                         e += wE * idx2 * (z.x * z.x + z.y * z.y);
                     }
                     if (f & (NF_MP | NF_PP)) {
-                        sincos_r<R>(dy * (S.ae ? cur.eb + cur.b : cur.b), &s, &c);
+                        sincos_r<R>(dy * (ae_ ? cur.eb + cur.b : cur.b), &s, &c);
                         const C z = gradc<R, C>(cur.p, s, c, nxt.p);
                         e += wN * idy2 * (z.x * z.x + z.y * z.y);
                     }
                 }
                 if (S.kappa2 > (R)0 && i < g.Nx - 1 && y < g.Ny - 1) {
                     R dB = -S.H;
-                    if (S.ae) dB += idx * (ebE - cur.eb) - idy * (nxt.ea - cur.ea);
+                    if (ae_) dB += idx * (ebE - cur.eb) - idy * (nxt.ea - cur.ea);
                     if (S.a) dB += idx * (bE - cur.b) - idy * (nxt.a - cur.a);
                     e += S.kappa2 * dB * dB;
                 }
@@ -149,12 +196,15 @@ k_cgf_update(CgfState<R> S, const typename V2<R>::type *__restrict__ dpsi, const
 }
 
 // ============================================================================= direction + coefficients
-template <typename R> struct RowD { typename V2<R>::type p, d; R a, b, ea, eb, da, db; };
+template <typename R> struct RawD { typename V2<R>::type p, d, g; R a, b, ea, eb, da, db, ga, gb; unsigned f; };
+template <typename R> struct RowD { typename V2<R>::type p, d; R a, b, ea, eb, da, db; unsigned f; };
 
 // NV = 5: c0..c4 (cg.h:400-467); NV = 17: c00..c04, c10..c14, c20..c24, c30, c40 (cg.h:528-701).
 // Quirk Q11: the coefficient kernels use the scalar eps only.
-template <typename R, int NV>
-__global__ void __launch_bounds__(CGF_THREADS, 2)
+// (the 17-coefficient fp64 variant runs 128-thread CTAs, three per SM: 170 registers per thread hold
+// the accumulators and three rows without spilling)
+template <typename R, int NV, bool EXT>
+__global__ void __launch_bounds__((NV == 17 && sizeof(R) == 8) ? 128 : CGF_THREADS, (NV == 17 && sizeof(R) == 8) ? 3 : 2)
 k_cgf_coef(CgfState<R> S, const double *__restrict__ beta, const typename V2<R>::type *__restrict__ gpsi,
            const R *__restrict__ ga, const R *__restrict__ gb, const typename V2<R>::type *__restrict__ dpsi_old,
            const R *__restrict__ da_old, const R *__restrict__ db_old, typename V2<R>::type *__restrict__ dpsi_new,
@@ -162,40 +212,55 @@ k_cgf_coef(CgfState<R> S, const double *__restrict__ beta, const typename V2<R>:
     typedef typename V2<R>::type C;
     constexpr bool SOLVEA = NV == 17;
     const Geo &g = S.g;
+    const R *const ae_ = EXT ? S.ae : nullptr, *const be_ = EXT ? S.be : nullptr;   // compile-time absent without an external potential
     const R dx = (R)g.dx, dy = (R)g.dy, idx = (R)g.idx, idy = (R)g.idy, idx2 = (R)g.idx2, idy2 = (R)g.idy2;
     const R beta_psi = (R)beta[0], beta_A = (R)beta[1];
     const int C1 = NV == 17 ? 5 : 1, C2 = NV == 17 ? 10 : 2, C3 = NV == 17 ? 15 : 3, C4 = NV == 17 ? 16 : 4;
     double v[NV];
 #pragma unroll
     for (int k = 0; k < NV; k++) v[k] = 0.0;
-    auto load = [&](int ii, int y) {
-        RowD<R> r;
-        r.p.x = 0; r.p.y = 0; r.d.x = 0; r.d.y = 0; r.a = 0; r.b = 0; r.ea = 0; r.eb = 0; r.da = 0; r.db = 0;
-        if (ii < g.Nx) {
+    auto loadraw = [&](int ii, int y) {
+        RawD<R> r;
+        r.p.x = 0; r.p.y = 0; r.d.x = 0; r.d.y = 0; r.g.x = 0; r.g.y = 0; r.a = 0; r.b = 0; r.ea = 0; r.eb = 0;
+        r.da = 0; r.db = 0; r.ga = 0; r.gb = 0; r.f = 0;
+        if (ii >= 0 && ii < g.Nx) {
             const size_t n = g.at(ii, y);
-            r.p = S.psi[n];
-            const C d = dpsi_old[n], gj = gpsi[n];
-            r.d.x = beta_psi * d.x - gj.x; r.d.y = beta_psi * d.y - gj.y;      // axmy_c (utils.h:97-104)
+            r.p = S.psi[n]; r.d = dpsi_old[n]; r.g = gpsi[n];
+            r.f = S.nf[n];
             if (S.a) { r.a = S.a[n]; r.b = S.b[n]; }
-            if (S.ae) { r.ea = S.ae[n]; r.eb = S.be[n]; }
-            if (SOLVEA) { r.da = beta_A * da_old[n] - ga[n]; r.db = beta_A * db_old[n] - gb[n]; }
+            if (ae_) { r.ea = ae_[n]; r.eb = be_[n]; }
+            if (SOLVEA) { r.da = da_old[n]; r.db = db_old[n]; r.ga = ga[n]; r.gb = gb[n]; }
         }
         return r;
     };
-    CGF_TILE_LOOP_BEGIN
-        RowD<R> cur = load(i, ys);
+    auto combine = [&](const RawD<R> &w) {
+        RowD<R> r;
+        r.p = w.p;
+        r.d.x = beta_psi * w.d.x - w.g.x; r.d.y = beta_psi * w.d.y - w.g.y;        // axmy_c (utils.h:97-104)
+        r.a = w.a; r.b = w.b; r.ea = w.ea; r.eb = w.eb; r.f = w.f;
+        r.da = 0; r.db = 0;
+        if (SOLVEA) { r.da = beta_A * w.da - w.ga; r.db = beta_A * w.db - w.gb; }
+        return r;
+    };
+    CGF_TILE_LOOP_BEGIN(31, 0)
+        CGF_PF_BEGIN
+            CGF_PF(S.psi, sizeof(C)) CGF_PF(dpsi_old, sizeof(C)) CGF_PF(gpsi, sizeof(C)) CGF_PF(S.a, sizeof(R))
+            CGF_PF(S.b, sizeof(R)) CGF_PF(da_old, sizeof(R)) CGF_PF(db_old, sizeof(R)) CGF_PF(ga, sizeof(R))
+            CGF_PF(gb, sizeof(R)) CGF_PF(ae_, sizeof(R)) CGF_PF(be_, sizeof(R)) CGF_PF(S.nf, 1)
+        CGF_PF_END
+        // combine row y+1 first, then refill the raw registers with row y+2: its loads are in flight
+        // while row y is evaluated (the 17 accumulators leave room for one raw row only)
+        RowD<R> cur = combine(loadraw(i, ys));
+        RawD<R> rawn = loadraw(i, ys + 1);
         for (int y = ys; y < ye; y++) {
-            const RowD<R> nxt = load(i, y + 1);
-            C pE = shfl_down_c<C>(cur.p), dE = shfl_down_c<C>(cur.d);
-            R bE = __shfl_down_sync(FULL, cur.b, 1), ebE = __shfl_down_sync(FULL, cur.eb, 1);
-            R dbE = __shfl_down_sync(FULL, cur.db, 1);
-            if (lane == 31) {
-                const RowD<R> e = load(i + 1, y);
-                pE = e.p; dE = e.d; bE = e.b; ebE = e.eb; dbE = e.db;
-            }
+            const RowD<R> nxt = combine(rawn);
+            rawn = loadraw(y + 2 <= ye ? i : -1, y + 2);
+            const C pE = shfl_down_c<C>(cur.p), dE = shfl_down_c<C>(cur.d);
+            const R bE = __shfl_down_sync(FULL, cur.b, 1), ebE = __shfl_down_sync(FULL, cur.eb, 1);
+            const R dbE = __shfl_down_sync(FULL, cur.db, 1);
             if (in) {
                 const size_t n = g.at(i, y);
-                const unsigned f = S.nf[n];
+                const unsigned f = cur.f;
                 if (f) {
                     R wW, wE, wS, wN, gw;
                     du_w<R>(f, wW, wE, wS, wN, gw);
@@ -213,7 +278,7 @@ k_cgf_coef(CgfState<R> S, const double *__restrict__ beta, const typename V2<R>:
                         if (!on) continue;
                         const R w = dir == 0 ? wE : wN, i2 = dir == 0 ? idx2 : idy2, d = dir == 0 ? dx : dy;
                         R ph = 0;
-                        if (S.ae) ph += d * (dir == 0 ? cur.ea : cur.eb);
+                        if (ae_) ph += d * (dir == 0 ? cur.ea : cur.eb);
                         if (S.a) ph += d * (dir == 0 ? cur.a : cur.b);
                         R s, c;
                         sincos_r<R>(ph, &s, &c);
@@ -257,7 +322,7 @@ k_cgf_coef(CgfState<R> S, const double *__restrict__ beta, const typename V2<R>:
                 if (S.kappa2 > (R)0 && i < g.Nx - 1 && y < g.Ny - 1) {
                     if (NV == 17) {
                         R BH = -S.H;
-                        if (S.ae) BH += idx * (ebE - cur.eb) - idy * (nxt.ea - cur.ea);
+                        if (ae_) BH += idx * (ebE - cur.eb) - idy * (nxt.ea - cur.ea);
                         if (S.a) BH += idx * (bE - cur.b) - idy * (nxt.a - cur.a);
                         const R dB = idx * (dbE - cur.db) - idy * (nxt.da - cur.da);
                         v[0] += (double)(S.kappa2 * BH * BH);
@@ -278,7 +343,9 @@ k_cgf_coef(CgfState<R> S, const double *__restrict__ beta, const typename V2<R>:
 }
 
 // ============================================================================= Jacobians + PR sums
-template <typename R> struct RowG { typename V2<R>::type p; R sa, ca, sb, cb; };
+// raw row data (loaded two rows ahead) and the same row with its two link variables evaluated
+template <typename R> struct RawG { typename V2<R>::type p; R pha, phb, eps; unsigned f; };
+template <typename R> struct RowG { typename V2<R>::type p; R sa, ca, sb, cb, eps; unsigned f; };
 
 // curl-curl stencils with the boundary doubling of quirk Q10 (cg.h:176-217, 240-282): direct loads
 // (they hit L1: the rows were just read for the link phases)
@@ -321,51 +388,67 @@ __device__ __forceinline__ R cgf_curl_b(const Geo &g, int i, size_t n, R H, cons
     return v;
 }
 
-template <typename R, bool SOLVEA, bool PREV>
+template <typename R, bool SOLVEA, bool PREV, bool EXT>
 __global__ void __launch_bounds__(CGF_THREADS, 2)
 k_cgf_grad(CgfState<R> S, typename V2<R>::type *__restrict__ gpsi, R *__restrict__ ga, R *__restrict__ gb,
            const typename V2<R>::type *__restrict__ ppsi, const R *__restrict__ pa, const R *__restrict__ pb,
            double *partials) {
     typedef typename V2<R>::type C;
     const Geo &g = S.g;
+    const R *const ae_ = EXT ? S.ae : nullptr, *const be_ = EXT ? S.be : nullptr;   // compile-time absent without an external potential
     const R dx = (R)g.dx, dy = (R)g.dy, idx = (R)g.idx, idy = (R)g.idy, idx2 = (R)g.idx2, idy2 = (R)g.idy2;
     double v[4] = {0.0, 0.0, 0.0, 0.0};
-    // psi and the two link variables owned by node (ii, y): exp(-i dx A_a), exp(-i dy A_b) as (sin, cos)
-    auto load = [&](int ii, int y) {
-        RowG<R> r;
-        r.p.x = 0; r.p.y = 0; r.sa = 0; r.ca = 1; r.sb = 0; r.cb = 1;
-        if (ii >= 0 && ii < g.Nx && y >= 0) {
+    // psi and the phases of the two links owned by node (ii, y)
+    auto loadraw = [&](int ii, int y) {
+        RawG<R> r;
+        r.p.x = 0; r.p.y = 0; r.pha = 0; r.phb = 0; r.eps = S.eps; r.f = 0;
+        if (ii >= 0 && ii < g.Nx) {
             const size_t n = g.at(ii, y);
-            const unsigned f = S.nf[n];
+            r.f = S.nf[n];
             r.p = S.psi[n];
-            if (f & (NF_PM | NF_PP)) {
-                R ph = 0;
-                if (S.ae) ph += S.ae[n];
-                if (S.a) ph += S.a[n];
-                sincos_r<R>(dx * ph, &r.sa, &r.ca);
-            }
-            if (f & (NF_MP | NF_PP)) {
-                R ph = 0;
-                if (S.be) ph += S.be[n];
-                if (S.b) ph += S.b[n];
-                sincos_r<R>(dy * ph, &r.sb, &r.cb);
-            }
+            R pa_ = 0, pb_ = 0;
+            if (ae_) { pa_ += ae_[n]; pb_ += be_[n]; }
+            if (S.a) { pa_ += S.a[n]; pb_ += S.b[n]; }
+            r.pha = dx * pa_; r.phb = dy * pb_;
+            if (S.epsf) r.eps = S.epsf[n];
         }
         return r;
     };
-    CGF_TILE_LOOP_BEGIN
-        RowG<R> prv = load(i, ys - 1);
-        RowG<R> cur = load(i, ys);
+    // exp(-i dx A_a), exp(-i dy A_b) as (sin, cos), only where the link carries weight
+    auto link = [&](const RawG<R> &w) {
+        RowG<R> r;
+        r.p = w.p; r.eps = w.eps; r.f = w.f;
+        r.sa = 0; r.ca = 1; r.sb = 0; r.cb = 1;
+        if (w.f & (NF_PM | NF_PP)) sincos_r<R>(w.pha, &r.sa, &r.ca);
+        if (w.f & (NF_MP | NF_PP)) sincos_r<R>(w.phb, &r.sb, &r.cb);
+        return r;
+    };
+    CGF_TILE_LOOP_BEGIN(30, 1)
+        CGF_PF_BEGIN
+            CGF_PF(S.psi, sizeof(C)) CGF_PF(S.a, sizeof(R)) CGF_PF(S.b, sizeof(R)) CGF_PF(ae_, sizeof(R))
+            CGF_PF(be_, sizeof(R)) CGF_PF(S.epsf, sizeof(R)) CGF_PF(S.nf, 1)
+            if (PREV) { CGF_PF(ppsi, sizeof(C)) CGF_PF(pa, sizeof(R)) CGF_PF(pb, sizeof(R)) }
+        CGF_PF_END
+        RowG<R> prv = link(loadraw(i, ys - 1));
+        RowG<R> cur = link(loadraw(i, ys));
+        RawG<R> rawn = loadraw(i, ys + 1);
         for (int y = ys; y < ye; y++) {
-            const RowG<R> nxt = load(i, y + 1);
-            C pE = shfl_down_c<C>(cur.p), pW = shfl_up_c<C>(cur.p);
-            R sW = __shfl_up_sync(FULL, cur.sa, 1), cW = __shfl_up_sync(FULL, cur.ca, 1);
-            if (lane == 31) { if (i + 1 < g.Nx) pE = S.psi[g.at(i + 1, y)]; else { pE.x = 0; pE.y = 0; } }
-            if (lane == 0) { const RowG<R> w = load(i - 1, y); pW = w.p; sW = w.sa; cW = w.ca; }
+            const RawG<R> raw2 = loadraw(y + 2 <= ye ? i : -1, y + 2);
+            // previous gradient of this node: issued now, used at the end of the iteration
+            C q; q.x = 0; q.y = 0;
+            R qa = 0, qb = 0;
+            if (PREV && in) {
+                const size_t n = g.at(i, y);
+                q = ppsi[n];
+                if (SOLVEA) { qa = pa[n]; qb = pb[n]; }
+            }
+            const RowG<R> nxt = link(rawn);
+            const C pE = shfl_down_c<C>(cur.p), pW = shfl_up_c<C>(cur.p);
+            const R sW = __shfl_up_sync(FULL, cur.sa, 1), cW = __shfl_up_sync(FULL, cur.ca, 1);
             if (in) {
                 const size_t n = g.at(i, y);
-                const unsigned f = S.nf[n];
-                const R eps = S.epsf ? S.epsf[n] : S.eps;
+                const unsigned f = cur.f;
+                const R eps = cur.eps;
                 const C p0 = cur.p;
                 C gj;
                 gj.x = 0; gj.y = 0;
@@ -398,36 +481,36 @@ k_cgf_grad(CgfState<R> S, typename V2<R>::type *__restrict__ gpsi, R *__restrict
                 gj.x *= dxdy; gj.y *= dxdy;
                 gpsi[n] = gj;
                 if (PREV) {
-                    const C q = ppsi[n];
                     v[0] += (double)(gj.x * (gj.x - q.x) + gj.y * (gj.y - q.y));
                     v[1] += (double)(q.x * q.x + q.y * q.y);
                 }
                 if (SOLVEA) {
                     const R pm = (f & NF_PM) ? (R)1 : (R)0, pp = (f & NF_PP) ? (R)1 : (R)0, mp = (f & NF_MP) ? (R)1 : (R)0;
                     if (i < g.Nx - 1) {
-                        R w = S.kappa2 * cgf_curl_a<R>(g, y, n, S.H, S.ae, S.be, S.a, S.b);
+                        R w = S.kappa2 * cgf_curl_a<R>(g, y, n, S.H, ae_, be_, S.a, S.b);
                         if (f & (NF_PM | NF_PP)) {
                             const R js = (p0.x * pE.y - p0.y * pE.x) * cur.ca - (p0.x * pE.x + p0.y * pE.y) * cur.sa;
                             w += -((R)0.5 * (pm + pp)) * idx * js;
                         }
                         w = (R)2.0 * dx * dy * w;
                         ga[n] = w;
-                        if (PREV) { const R q = pa[n]; v[2] += (double)(w * (w - q)); v[3] += (double)(q * q); }
+                        if (PREV) { v[2] += (double)(w * (w - qa)); v[3] += (double)(qa * qa); }
                     }
                     if (y < g.Ny - 1) {
-                        R w = S.kappa2 * cgf_curl_b<R>(g, i, n, S.H, S.ae, S.be, S.a, S.b);
+                        R w = S.kappa2 * cgf_curl_b<R>(g, i, n, S.H, ae_, be_, S.a, S.b);
                         if (f & (NF_MP | NF_PP)) {
                             const R js = (p0.x * nxt.p.y - p0.y * nxt.p.x) * cur.cb - (p0.x * nxt.p.x + p0.y * nxt.p.y) * cur.sb;
                             w += -((R)0.5 * (mp + pp)) * idy * js;
                         }
                         w = (R)2.0 * dx * dy * w;
                         gb[n] = w;
-                        if (PREV) { const R q = pb[n]; v[2] += (double)(w * (w - q)); v[3] += (double)(q * q); }
+                        if (PREV) { v[2] += (double)(w * (w - qb)); v[3] += (double)(qb * qb); }
                     }
                 }
             }
             prv = cur;
             cur = nxt;
+            rawn = raw2;
         }
     CGF_TILE_LOOP_END
     if (PREV) block_sum_to_partials<4>(v, partials, blockIdx.x);
@@ -443,9 +526,19 @@ __global__ void k_cgf_beta(const double *__restrict__ sums, double *beta) {
 }
 
 // ----------------------------------------------------------------------------- host side
-static int cgf_grid(svl_ctx *c) {
+// rows per strip: 32 where that still leaves a few tiles per resident CTA, fewer on small grids
+static int cgf_rows(const svl_ctx *c) {
     const Geo &g = c->g;
-    int ntiles = ((g.Nx + 31) / 32) * ((g.j1 - g.j0 + CGF_WARPS * CGF_V - 1) / (CGF_WARPS * CGF_V));
+    for (int V = 32; V > 4; V >>= 1) {
+        long tiles = (long)((g.Nx + 30 * CGF_WARPS - 1) / (30 * CGF_WARPS)) * ((g.j1 - g.j0 + V - 1) / V);
+        if (tiles >= 148 * 2 * 2) return V;
+    }
+    return 4;
+}
+static int cgf_grid(svl_ctx *c, int warps = CGF_WARPS) {
+    const Geo &g = c->g;
+    const int V = cgf_rows(c);
+    int ntiles = ((g.Nx + 30 * warps - 1) / (30 * warps)) * ((g.j1 - g.j0 + V - 1) / V);
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
     int cap = nsm * 2 * 4;                       // a few waves of resident CTAs: balances the tail, ~1200 partials
@@ -458,6 +551,7 @@ static CgfState<R> cgf_state(svl_ctx *c, double kappa2, double eps, const svl_bu
     typedef typename V2<R>::type C;
     CgfState<R> S;
     S.g = c->g;
+    S.V = cgf_rows(c);
     S.kappa2 = (R)kappa2; S.eps = (R)eps; S.H = (R)H;
     S.epsf = epsf ? (const R *)epsf->p[0] : nullptr;
     S.nf = c->nf;
@@ -477,11 +571,18 @@ static int cgf_begin_t(svl_ctx *c, int solveA, int have_prev, double kappa2, dou
     CgfState<R> S = cgf_state<R>(c, kappa2, eps, epsf, H, psi, abei, ab);
     R *gA0 = solveA ? (R *)g_A->p[0] : nullptr, *gA1 = solveA ? (R *)g_A->p[1] : nullptr;
     const R *pA0 = solveA ? (const R *)g_A_prev->p[0] : nullptr, *pA1 = solveA ? (const R *)g_A_prev->p[1] : nullptr;
+    const bool ext = abei != nullptr;
 #define GRAD_ARGS S, (C *)g_psi->p[0], gA0, gA1, (const C *)g_psi_prev->p[0], pA0, pA1, c->partials
-    if (solveA && have_prev) k_cgf_grad<R, true, true><<<nb, CGF_THREADS, 0, c->stream>>>(GRAD_ARGS);
-    else if (solveA) k_cgf_grad<R, true, false><<<nb, CGF_THREADS, 0, c->stream>>>(GRAD_ARGS);
-    else if (have_prev) k_cgf_grad<R, false, true><<<nb, CGF_THREADS, 0, c->stream>>>(GRAD_ARGS);
-    else k_cgf_grad<R, false, false><<<nb, CGF_THREADS, 0, c->stream>>>(GRAD_ARGS);
+#define GRAD_LAUNCH(SA, PV)                                                                               \
+    do {                                                                                                  \
+        if (ext) k_cgf_grad<R, SA, PV, true><<<nb, CGF_THREADS, 0, c->stream>>>(GRAD_ARGS);               \
+        else k_cgf_grad<R, SA, PV, false><<<nb, CGF_THREADS, 0, c->stream>>>(GRAD_ARGS);                  \
+    } while (0)
+    if (solveA && have_prev) GRAD_LAUNCH(true, true);
+    else if (solveA) GRAD_LAUNCH(true, false);
+    else if (have_prev) GRAD_LAUNCH(false, true);
+    else GRAD_LAUNCH(false, false);
+#undef GRAD_LAUNCH
 #undef GRAD_ARGS
     SVL_CHECK(cudaGetLastError());
     c->stat_launches += 1;
@@ -502,22 +603,24 @@ static int cgf_begin_t(svl_ctx *c, int solveA, int have_prev, double kappa2, dou
     if (solveA) SVL_TRY(svl_scratch_edge(c, 0, &dn_A));
     // Quirk Q11: the coefficient kernels use the scalar eps (0.0 when eps is a field)
     S.eps = (R)(epsf ? 0.0 : eps);
-    if (solveA) {
-        k_cgf_coef<R, 17><<<nb, CGF_THREADS, 0, c->stream>>>(S, dbeta, (const C *)g_psi->p[0], gA0, gA1,
-                                                           (const C *)d_psi->p[0], (const R *)d_A->p[0],
-                                                           (const R *)d_A->p[1], (C *)dn_psi->p[0], (R *)dn_A->p[0],
-                                                           (R *)dn_A->p[1], c->partials);
-    } else {
-        k_cgf_coef<R, 5><<<nb, CGF_THREADS, 0, c->stream>>>(S, dbeta, (const C *)g_psi->p[0], nullptr, nullptr,
-                                                          (const C *)d_psi->p[0], nullptr, nullptr, (C *)dn_psi->p[0],
-                                                          nullptr, nullptr, c->partials);
-    }
+#define COEF17_ARGS S, dbeta, (const C *)g_psi->p[0], gA0, gA1, (const C *)d_psi->p[0], (const R *)d_A->p[0],  \
+                    (const R *)d_A->p[1], (C *)dn_psi->p[0], (R *)dn_A->p[0], (R *)dn_A->p[1], c->partials
+#define COEF5_ARGS S, dbeta, (const C *)g_psi->p[0], nullptr, nullptr, (const C *)d_psi->p[0], nullptr, nullptr,     \
+                   (C *)dn_psi->p[0], nullptr, nullptr, c->partials
+    const int nt17 = sizeof(R) == 8 ? 128 : CGF_THREADS, nb17 = sizeof(R) == 8 ? cgf_grid(c, 4) * 3 / 2 : nb;
+    if (solveA) SVL_TRY(svl_ensure_partials(c, (size_t)nb17 * 17));
+    if (solveA && ext) k_cgf_coef<R, 17, true><<<nb17, nt17, 0, c->stream>>>(COEF17_ARGS);
+    else if (solveA) k_cgf_coef<R, 17, false><<<nb17, nt17, 0, c->stream>>>(COEF17_ARGS);
+    else if (ext) k_cgf_coef<R, 5, true><<<nb, CGF_THREADS, 0, c->stream>>>(COEF5_ARGS);
+    else k_cgf_coef<R, 5, false><<<nb, CGF_THREADS, 0, c->stream>>>(COEF5_ARGS);
+#undef COEF17_ARGS
+#undef COEF5_ARGS
     SVL_CHECK(cudaGetLastError());
     c->stat_launches += 1;
     SVL_TRY(svl_swap(c, d_psi, dn_psi));
     if (solveA) SVL_TRY(svl_swap(c, d_A, dn_A));
     SVL_CHECK(cudaMemcpyAsync(c->h_result + 32, dbeta, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    SVL_TRY(svl_finish_sum(c, nb, solveA ? 17 : 5, (double)((R)c->g.dx * (R)c->g.dy), c_out));   // one host sync
+    SVL_TRY(svl_finish_sum(c, solveA ? nb17 : nb, solveA ? 17 : 5, (double)((R)c->g.dx * (R)c->g.dy), c_out));   // one host sync
     beta[0] = c->h_result[32];
     if (solveA) beta[1] = c->h_result[33];
     return 0;
@@ -534,14 +637,17 @@ static int cgf_end_t(svl_ctx *c, int solveA, double kappa2, double eps, const sv
     svl_buf *pn = nullptr, *An = nullptr;
     SVL_TRY(svl_scratch_node(c, 0, &pn));
     if (solveA) SVL_TRY(svl_scratch_edge(c, 0, &An));
-    if (solveA)
-        k_cgf_update<R, true><<<nb, CGF_THREADS, 0, c->stream>>>(S, (const C *)d_psi->p[0], (const R *)d_A->p[0],
-                                                                (const R *)d_A->p[1], (R)alpha_psi, (R)alpha_A,
-                                                                (C *)pn->p[0], (R *)An->p[0], (R *)An->p[1], c->partials);
-    else
-        k_cgf_update<R, false><<<nb, CGF_THREADS, 0, c->stream>>>(S, (const C *)d_psi->p[0], nullptr, nullptr,
-                                                                 (R)alpha_psi, (R)0, (C *)pn->p[0], nullptr, nullptr,
-                                                                 c->partials);
+    const bool ext = abei != nullptr;
+#define UPD_A_ARGS S, (const C *)d_psi->p[0], (const R *)d_A->p[0], (const R *)d_A->p[1], (R)alpha_psi, (R)alpha_A,  \
+                   (C *)pn->p[0], (R *)An->p[0], (R *)An->p[1], c->partials
+#define UPD_P_ARGS S, (const C *)d_psi->p[0], nullptr, nullptr, (R)alpha_psi, (R)0, (C *)pn->p[0], nullptr, nullptr, \
+                   c->partials
+    if (solveA && ext) k_cgf_update<R, true, true><<<nb, CGF_THREADS, 0, c->stream>>>(UPD_A_ARGS);
+    else if (solveA) k_cgf_update<R, true, false><<<nb, CGF_THREADS, 0, c->stream>>>(UPD_A_ARGS);
+    else if (ext) k_cgf_update<R, false, true><<<nb, CGF_THREADS, 0, c->stream>>>(UPD_P_ARGS);
+    else k_cgf_update<R, false, false><<<nb, CGF_THREADS, 0, c->stream>>>(UPD_P_ARGS);
+#undef UPD_A_ARGS
+#undef UPD_P_ARGS
     SVL_CHECK(cudaGetLastError());
     c->stat_launches += 1;
     SVL_TRY(svl_swap(c, psi, pn));

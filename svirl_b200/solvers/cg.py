@@ -51,7 +51,7 @@ class CG(object):
         eps = float(np.asarray(p.linear_coefficient_scalar_h()).reshape(-1)[0])
         return dict(k2=float(p.gl_parameter_squared_h()), eps=eps, epsf=_h(p.linear_coefficient_h()),
                     H=float(p.homogeneous_external_field), psi=self.vars.order_parameter_h().handle,
-                    abei=_h(p.external_irregular_vector_potential_h()), ab=_h(self.vars.vector_potential_h()))
+                    abei=_h(p._external_irregular_for_kernels()), ab=_h(self.vars.vector_potential_h()))
 
     # ---- kernel-level private API used by the reference's tests
     @property
