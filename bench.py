@@ -212,6 +212,8 @@ def bench_cg(args, wl, gl, par, N):
     region because it is part of an iteration."""
     from svirl_b200 import _lib
     gl.solve.td(dt=0.1, Nt=20)
+    if N >= 8192 * 8192:
+        gl.cfg.cg_line_search = "normalized"           # SciPy BFGS runs away on raw coefficients of this size
     gl.cfg.convergence_rtol = 0.0
     gl.solve._init_cg()
     gl.solve._cg._CG__convergence_rtol = -1.0          # never stop early: time exactly K iterations
@@ -242,16 +244,38 @@ def bench_cg(args, wl, gl, par, N):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = per_iter * N * args.steps / (ms.value * 1e-3) / 1e9
     E = gl.solve._cg.cg_energies
+    cpu = None
+    if not args.no_cpu_baseline:
+        # NumPy port of the same iteration on a bounded sample: a 768^2 sub-problem with the same
+        # parameters (the cost per node does not depend on the grid size), scaled to this grid
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import glnumpy as O
+        ns = 768
+        og = O.Grid(ns, ns, 0.5, 0.5, wl["dtype"])
+        op = O.initial_psi(og, 1.0, 1234)
+        oa, ob = O.initial_A(og, wl["H"])
+        omt = hole_tiling(ns, ns) if wl["tiling"] else None
+        op, oa, ob, _ = O.td_run(og, 0.1, 3, 1.0, omt, wl["kappa"], wl["sigma"], wl["H"], op, oa, ob, rand_t=1234)
+        tc = time.perf_counter()
+        nit = 3
+        O.cg_run(og, nit, wl["kappa"], 1.0, wl["H"], omt, op, np.zeros_like(oa), np.zeros_like(ob), oa, ob, rtol=-1.0)
+        tc = time.perf_counter() - tc
+        cpu = {"value": nit / tc * (ns * ns) / N, "unit": "iterations/s", "cores": 1, "kind": "port",
+               "sample": "%d NumPy-oracle CG iterations on a 768^2 grid with the same parameters (%.1f s), "
+                         "scaled by the node ratio to %dx%d" % (nit, tc, wl["Nx"], wl["Ny"])}
     line = {"metric": "cg_iters_per_s", "value": args.steps / (ms.value * 1e-3), "unit": "iterations/s", "n_gpus": 1,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms.value / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if wl["dtype"] is np.float32 else "f64", "data": "synthetic",
-            "config": {"workload": wl["name"], "Nx": wl["Nx"], "Ny": wl["Ny"], "seed": 1234},
+            "config": {"workload": wl["name"], "Nx": wl["Nx"], "Ny": wl["Ny"], "seed": 1234,
+                       "line_search": gl.cfg.cg_line_search},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "bytes_per_node_iter": per_iter,
                          "note": "algorithmic bytes = fused lower bound of SURVEY 8d; includes the host line search time"},
-            "cpu_baseline": None, "clocks": clocks, "gpu_launches": int(launches),
-            "wall_ms_per_iter": 1e3 * wall / args.steps, "energy_first_last": [float(E[0]), float(E[-1])],
+            "cpu_baseline": cpu, "clocks": clocks, "gpu_launches": int(launches),
+            "wall_ms_per_iter": 1e3 * wall / args.steps, "energy_first_last": [float(E[0]), float(E[-1])], "energies": [float(e) for e in E],
+            "energy_decreasing": bool(np.all(np.diff(np.array(E, dtype=np.float64)) < 0)),
+            "line_search_rescues": int(gl.solve._cg.line_search_rescues),
             "e2e": {"value": args.steps / wall, "unit": "iterations/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 8 * (17 if finite else 5) + 8,
                     "api": "gl.solve.cg(): per iteration the 5/17 coefficients and the energy come back to the host"}}

@@ -34,6 +34,9 @@ dtype_complex = None
 stop_criterion_order_parameter = 1e-6
 stop_criterion_vector_potential = 1e-6
 convergence_rtol = 1e-6
+# new (not in the reference): 'reference' = SciPy BFGS on the raw coefficients with a rescue when it
+# runs away, 'normalized' = always minimise c / max|c| (robust on very large grids)
+cg_line_search = 'reference'
 
 # slab decomposition (new): rows [j0, j1) of the global grid are owned by this process
 slab = None

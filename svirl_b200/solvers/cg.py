@@ -41,6 +41,7 @@ class CG(object):
             self.__gdir_A, self.__gjac_A, self.__gjac_A_prev = Z(_lib.EDGE), Z(_lib.EDGE), Z(_lib.EDGE)
         self.__c = np.zeros((5, 5), dtype=cfg.dtype) if solveA else np.zeros(5, dtype=cfg.dtype)
         self.cg_energies = []
+        self.line_search_rescues = 0      # times the reference's BFGS call ran away and was redone on c / N
 
     # ---- argument helpers
     def _state(self):
@@ -119,6 +120,44 @@ class CG(object):
         r = scipy.optimize.minimize(f, x0=np.array(alpha0), jac=j, method='BFGS', tol=tol)
         return r.x
 
+    def _cg_alpha_min_scaled(self):
+        """The same BFGS minimisation on c / max|c| (an O(1) objective)."""
+        c = self.__c
+        scale = float(np.max(np.abs(c)))
+        if not np.isfinite(scale) or scale == 0.0:
+            return self._cg_alpha_min()
+        self.__c = c / scale
+        try:
+            return self._cg_alpha_min()
+        finally:
+            self.__c = c
+
+    def _cg_alpha_min_guarded(self):
+        """The reference's BFGS call, plus a rescue for the case where it runs away.
+
+        SciPy's BFGS is not invariant under scaling of the objective: with the coefficients of a
+        large grid (they grow with the number of nodes; observed from 8192^2 upwards) its line
+        search can leave the basin of the 4th-order polynomial, which is unbounded below in
+        alpha_A, and return |alpha| ~ 1e35 -- the state is lost (NaN) from then on, in the
+        reference exactly as here.  Whenever the reference result is unusable (not finite, huge,
+        or no decrease) the same minimisation is repeated on the normalised polynomial
+        c / max|c|, which converges to the local minimum next to alpha = 0.  Runs in which the
+        reference call works are unaffected, so trajectory parity holds wherever the reference
+        itself survives.  ``cfg.cg_line_search = 'normalized'`` (not a reference option) uses the
+        normalised polynomial in every iteration."""
+        if getattr(cfg, 'cg_line_search', 'reference') == 'normalized':
+            return self._cg_alpha_min_scaled()
+        c = self.__c
+        P = np.polynomial.polynomial
+        with np.errstate(all='ignore'):
+            a = self._cg_alpha_min()
+            ok = np.all(np.isfinite(a)) and np.max(np.abs(a)) < 1.0e6
+            ok = ok and P.polyval2d(a[0], a[1], c) <= c[0, 0]
+        if ok:
+            return a
+        self.line_search_rescues += 1
+        return self._cg_alpha_min_scaled()
+
     # ---- the two minimisation loops
     def _iterate(self, n_iter, solveA):
         s = self._state()
@@ -139,7 +178,7 @@ class CG(object):
             r = np.array(cbuf[:], dtype=cfg.dtype)
             if solveA:
                 self._store_c17(r)
-                alpha_psi, alpha_A = self._cg_alpha_min()
+                alpha_psi, alpha_A = self._cg_alpha_min_guarded()
             else:
                 self.__c[:] = r
                 alpha_psi, alpha_A = self._cg_alpha_psi_min(), 0.0

@@ -371,3 +371,30 @@ def test_cg_fused_iteration_equals_kernel_composition(case):
     tol = (1e-7 if "kinf" not in case else 1e-11) if f64 else 2e-3
     for k in (2, 3, 4):
         assert np.abs(res[0][k] - res[1][k]).max() < tol
+
+
+def test_cg_line_search_rescue_on_large_grid_coefficients():
+    """Coefficients measured at 16384^2 (per node, scaled back up): the reference's SciPy BFGS call
+    runs away to |alpha| ~ 1e35 on them; the guarded line search detects that and returns the local
+    minimum next to alpha = 0 (the one BFGS finds on the per-node polynomial)."""
+    from svirl_b200 import GLSolver
+    gl = GLSolver(Nx=16, Ny=16, dx=0.5, dy=0.5, gl_parameter=2.0)
+    gl.solve._init_cg()
+    cg = gl.solve._cg
+    c = np.array([[-5.569412e-02, -5.033755e-03, 7.153037e-02, 2.296557e-04, -4.050537e-04],
+                  [-2.623664e-02, -1.681635e-02, 2.434797e-02, 1.979796e-04, -2.142220e-04],
+                  [2.284921e-02, -3.724204e-03, 5.584273e-03, 3.571101e-05, -4.655317e-05],
+                  [1.439366e-02, 0, 0, 0, 0], [2.060112e-03, 0, 0, 0, 0]])
+    cg._CG__c[:] = c * 16384.0 ** 2
+    with np.errstate(all="ignore"):
+        raw = cg._cg_alpha_min()
+    assert not (np.all(np.isfinite(raw)) and np.max(np.abs(raw)) < 1e6)       # the reference call is unusable here
+    a = cg._cg_alpha_min_guarded()
+    assert cg.line_search_rescues == 1
+    assert np.allclose(a, [0.42212742, 0.07723854], rtol=1e-4)
+    gl.cfg.cg_line_search = "normalized"
+    assert np.allclose(cg._cg_alpha_min_guarded(), [0.42212742, 0.07723854], rtol=1e-4) and cg.line_search_rescues == 1
+    gl.cfg.cg_line_search = "reference"
+    # well-scaled coefficients: the reference call is kept as is
+    cg._CG__c[:] = c
+    assert np.allclose(cg._cg_alpha_min_guarded(), cg._cg_alpha_min(), rtol=0, atol=0) and cg.line_search_rescues == 1
