@@ -93,43 +93,75 @@ def bytes_per_node_sweep(wl):
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler(object):
+    """SM clock and throttle reasons sampled while the timed region runs: NVML in-process (a sample
+    every ~2 ms, so even a 20 ms region is covered), nvidia-smi as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.samples, self.stop_flag, self.th = index, [], False, None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates all GPUs of the box; CUDA_VISIBLE_DEVICES may remap the torch index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [x.strip() for x in vis.split(",") if x.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
-    def _run(self):
+    def _run_nvml(self):
+        n = self.nvml
+        R = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        try:
+            mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append([sm, mx, [k for k, v in R.items() if bits & v]])
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _run_smi(self):
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.samples.append([x.strip() for x in out.strip().split(",")])
+                s = [x.strip() for x in out.strip().split(",")]
+                names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+                self.samples.append([float(s[0]), float(s[1]),
+                                     [k for k, v in zip(names, s[3:7]) if v.lower().startswith("active")]])
             except Exception:
                 pass
             time.sleep(0.05)
 
     def start(self):
-        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th = threading.Thread(target=self._run_nvml if self.nvml else self._run_smi, daemon=True)
         self.th.start()
 
     def stop(self):
         self.stop_flag = True
         if self.th:
             self.th.join(timeout=10)
-        sm, reasons, mx = [], set(), None
-        for s in self.samples:
-            try:
-                sm.append(float(s[0]))
-                mx = float(s[1])
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        sm = [s[0] for s in self.samples]
+        mx = next((s[1] for s in self.samples if s[1]), None)
+        reasons = sorted({r for s in self.samples for r in s[2]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": reasons,
+                "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------ CPU reference arm
@@ -151,6 +183,13 @@ def cpu_reference_steps(wl, nsteps, warmup=0):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import glnumpy as O
     Nx, Ny, dt_ = wl["Nx"], wl["Ny"], wl["dtype"]
+    band = None
+    if (warmup + nsteps) > 60 and Ny > 512:
+        # bounded sample: a 512-row band of the same workload per step (same cost per node), so that
+        # a long --steps run still ends within a few minutes
+        band = 512
+        Ny = band
+        wl = dict(wl, Ny=band)
     g = O.Grid(Nx, Ny, 0.5, 0.5, dt_)
     psi = O.initial_psi(g, 1.0, 1234)
     a, b = O.initial_A(g, wl["H"])
@@ -168,7 +207,7 @@ def cpu_reference_steps(wl, nsteps, warmup=0):
             psi, n = O.td_psi_solve(g, 0.1, eps, mt, a, b, psi)
             sweeps += n
         el = time.perf_counter() - t0
-        return N * nsteps / el, dict(kind="port", cores=1, sweeps=sweeps, seconds=el)
+        return N * nsteps / el, dict(kind="port", cores=1, sweeps=sweeps, seconds=el, band=band)
     lib = C.CDLL(so)
     fn = lib.simt_launch_iterate_order_parameter_jacobi_step
     real = C.c_float if dt_ is np.float32 else C.c_double
@@ -201,7 +240,7 @@ def cpu_reference_steps(wl, nsteps, warmup=0):
             if 1.0e-4 * float(r2[0]) < 1.0:
                 break
     el = time.perf_counter() - t0
-    return N * nsteps / el, dict(kind="reference", cores=os.cpu_count(), sweeps=sweeps, seconds=el)
+    return N * nsteps / el, dict(kind="reference", cores=os.cpu_count(), sweeps=sweeps, seconds=el, band=band)
 
 
 # ------------------------------------------------------------------------------------ CG mode
@@ -286,8 +325,8 @@ def bench_cg(args, wl, gl, par, N):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--psi-kernel", type=int, default=None)
@@ -317,7 +356,9 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if wl["dtype"] is np.float32 else "f64", "data": "synthetic", "config": cfgd,
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
-                                 "sample": "%d full-grid TDGL steps (%d Jacobi sweeps)" % (args.steps, info["sweeps"])},
+                                 "sample": "%d TDGL steps on %s (%d Jacobi sweeps)"
+                                           % (args.steps, "a %d-row band of the grid per step" % info["band"]
+                                              if info.get("band") else "the full grid", info["sweeps"])},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -416,15 +457,20 @@ def main():
     bpsi, bA = bytes_per_node_sweep(wl)
     alg_bytes = (sw_psi * bpsi + sw_A * bA) * (N // world)      # per GPU: the roofline is a per-device quantity
     achieved = alg_bytes / (t_ms * 1e-3) / 1e9
+    # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this command
+    # (profiles/r01_ncu_psi_tile_f32_k4_cfg2.txt: dram__bytes_read.sum + dram__bytes_write.sum)
+    traffic = 122.6e6 if (args.workload == "cfg2" and world == 1 and args.psi_kernel in (None, 2)
+                          and args.psi_k in (None, 4)) else None
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650",
+            "traffic": traffic, "traffic_note": "bytes per 4-sweep launch (ncu); algorithmic bytes of the same launch: "
+                                                "%d" % (4 * bpsi * (N // world)), "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650",
             "kernel": "psi Jacobi sweep", "bytes_per_node_sweep": bpsi, "sweeps_psi": int(sw_psi),
             "sweeps_A": int(sw_A), "launches": int(launches),
             "avg_launch_us": 1e3 * t_ms / max(launches, 1)}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        nst = 2 if N >= 2048 * 2048 else 5
+        nst = 25 if N <= 2048 * 2048 else 2            # ~10 s of host work at cfg2
         v, info = cpu_reference_steps(wl, nst, 0)
         cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                "sample": "%d full-grid TDGL steps from the seeded initial state (%d Jacobi sweeps, %.1f s)"

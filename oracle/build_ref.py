@@ -125,6 +125,7 @@ def prebuild(dtype, Nx, Ny, dx, dy, rvl):
 # configurations bench.py's CPU baseline uses (cfg2 sample sizes)
 PREBUILD = [
     (np.float32, 2048, 2048, 0.5, 0.5, 5),
+    (np.float32, 2048, 512, 0.5, 0.5, 5),      # row-band sample of cfg2 for long --impl reference runs
     (np.float32, 512, 512, 0.5, 0.5, 5),
     (np.float64, 129, 129, 0.5, 0.5, 17),
 ]
