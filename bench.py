@@ -332,6 +332,8 @@ def main():
     ap.add_argument("--psi-kernel", type=int, default=None)
     ap.add_argument("--psi-k", type=int, default=None)
     ap.add_argument("--a-kernel", type=int, default=None)
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (svl_set_option)")
+    ap.add_argument("--ny-mult", type=int, default=1, help="multiply Ny (to run an N-GPU weak-scaling grid on fewer GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -340,6 +342,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     wl = workload(args.workload)
+    if args.ny_mult > 1:
+        wl = dict(wl, Ny=wl["Ny"] * args.ny_mult, name=wl["name"] + " (Ny x%d)" % args.ny_mult)
     if world > 1 and args.impl == "ours":
         wl = dict(wl, Ny=wl["Ny"] * world, name=wl["name"] + " x%d row slabs (Ny=%d)" % (world, wl["Ny"] * world))
     N = wl["Nx"] * wl["Ny"]
@@ -379,6 +383,9 @@ def main():
         par.set_option("psi_k", args.psi_k)
     if args.a_kernel is not None:
         par.set_option("a_kernel", args.a_kernel)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        par.set_option(k, int(v))
     td_kw = dict(dt=0.1)
     if wl.get("cg"):
         return bench_cg(args, wl, gl, par, N)

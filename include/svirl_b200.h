@@ -61,6 +61,9 @@ int svl_set_option(svl_ctx *ctx, const char *name, int value);
 int svl_get_stat(svl_ctx *ctx, const char *name, double *value);
 /* self-test hook: the library's own sincos (used for every link variable exp(-i d A)) on n values */
 int svl_debug_sincos(svl_ctx *ctx, size_t n, const double *x, double *s_out, double *c_out);
+/* diagnostics for slab runs (option "trace" = N arms it): per psi-tile launch {first CTA start, last CTA
+ * end, longest halo-flag wait, end of the last wait} in %globaltimer nanoseconds */
+int svl_debug_trace(svl_ctx *ctx, unsigned long long *out, int max_records, int *n_out);
 /* CUDA events on the context's launch stream (8 slots), for device-side timing */
 int svl_event_record(svl_ctx *ctx, int slot);
 int svl_event_elapsed_ms(svl_ctx *ctx, int slot0, int slot1, double *ms);
@@ -177,6 +180,12 @@ int svl_sum_v(svl_ctx *ctx, const svl_buf *in, size_t nv, int ne, double *out /*
 int svl_slab_export(svl_ctx *ctx, svl_buf *psi, svl_buf *ab, void *handles_out);
 int svl_slab_connect(svl_ctx *ctx, const void *lo_handles, int lo_j0, const void *hi_handles, int hi_j0);
 int svl_slab_exchange(svl_ctx *ctx, svl_buf *buf);
+/* Residual board (optional, replaces the callbacks below when connected): every rank exports one
+ * 64-byte CUDA IPC handle, all ranks connect with the world x 64 bytes in rank order; the MAX of the
+ * residual slots is then taken by one small kernel over peer memory (option "resid_board" = 0
+ * switches back to the callbacks). */
+int svl_slab_board_export(svl_ctx *ctx, void *handle_out);
+int svl_slab_board_connect(svl_ctx *ctx, int rank, int world, const void *handles);
 int svl_set_reduce_callback(svl_ctx *ctx, void (*reduce_max_u64)(unsigned long long *vals, int n));
 /* same on device words, with the reduction enqueued on the context's stream (svl_get_stream) */
 int svl_set_reduce_callback_device(svl_ctx *ctx, void (*reduce_max_dev)(unsigned long long *dvals, int n));

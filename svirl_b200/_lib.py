@@ -23,6 +23,7 @@ SIGNATURES = {
     "svl_set_option": ([_p, C.c_char_p, _i], _i),
     "svl_get_stat": ([_p, C.c_char_p, _pd], _i),
     "svl_debug_sincos": ([_p, _sz, _pd, _pd, _pd], _i),
+    "svl_debug_trace": ([_p, C.POINTER(C.c_ulonglong), _i, C.POINTER(_i)], _i),
     "svl_event_record": ([_p, _i], _i),
     "svl_event_elapsed_ms": ([_p, _i, _i, _pd], _i),
     "svl_alloc": ([_p, _i, _sz, _i, C.POINTER(_p)], _i),
@@ -59,6 +60,8 @@ SIGNATURES = {
     "svl_slab_export": ([_p, _p, _p, _p], _i),
     "svl_slab_connect": ([_p, _p, _i, _p, _i], _i),
     "svl_slab_exchange": ([_p, _p], _i),
+    "svl_slab_board_export": ([_p, _p], _i),
+    "svl_slab_board_connect": ([_p, _i, _i, _p], _i),
     "svl_set_reduce_callback": ([_p, _p], _i),
     "svl_set_reduce_callback_device": ([_p, _p], _i),
     "svl_get_stream": ([_p], _p),

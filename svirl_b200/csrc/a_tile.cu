@@ -35,6 +35,8 @@ struct ATileArgs {
     const unsigned long long *wait_flags;
     unsigned long long wait_epoch;
     int has_lo, has_hi;
+    SlabPush push;                 // slabs: in-kernel push of the output's boundary rows
+    int push_expect[2];
 };
 
 __device__ __forceinline__ uint32_t a_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -64,7 +66,7 @@ struct ASmem {
     static constexpr uint32_t tx_bytes = (uint32_t)((sizeof(C) + 2 * sizeof(R)) * NN);
 };
 
-template <typename R, int K, int TXE, int V, int NB, int MODE>
+template <typename R, int K, int TXE, int V, int NB, int MODE, bool SLAB>
 __global__ void __launch_bounds__(TXE *NB, (TXE * NB > 256 ? 1 : 2))
 k_a_tile(const __grid_constant__ ATileArgs A, const __grid_constant__ CUtensorMap tm_psi,
          const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b) {
@@ -84,8 +86,13 @@ k_a_tile(const __grid_constant__ ATileArgs A, const __grid_constant__ CUtensorMa
     const int tid = threadIdx.x;
     const int col = tid % TXE, band = tid / TXE;
     const int r0 = band * V;
-    const int ntx = (g.Nx + TX - 1) / TX;
-    const int bx = blockIdx.x % ntx, by = blockIdx.x / ntx;
+    const int ntx = (g.Nx + TX - 1) / TX, nty = (g.j1 - g.j0 + TYO - 1) / TYO;
+    // slabs: the first / last tile row (the only tiles that read a neighbour's halo rows) get the
+    // lowest block indices: they run first (the neighbour's previous push landed a launch ago, so the
+    // flag wait is free) and this launch's push leaves early
+    int tile = blockIdx.x;
+    if (SLAB && nty > 2) tile = tile < ntx ? tile : (tile < 2 * ntx ? (nty - 1) * ntx + (tile - ntx) : tile - ntx);
+    const int bx = tile % ntx, by = tile / ntx;
     const int xg0 = bx * TX - H, yg0 = g.j0 + by * TYO - K;
     const int x = xg0 + col;
 
@@ -93,9 +100,10 @@ k_a_tile(const __grid_constant__ ATileArgs A, const __grid_constant__ CUtensorMa
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a_smem_u32(bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (A.wait_flags) {                                // slabs: the neighbours' halo rows of the input have arrived
+        if (SLAB) {                                        // slabs: the neighbours' halo rows of the input have arrived
             for (int sdir = 0; sdir < 2; sdir++) {
                 if (!(sdir == 0 ? A.has_lo : A.has_hi)) continue;
+                if (by != (sdir == 0 ? 0 : nty - 1)) continue;          // interior tile: nothing to wait for
                 unsigned long long v = 0;
                 long long t0 = clock64();
                 do {
@@ -249,16 +257,40 @@ k_a_tile(const __grid_constant__ ATileArgs A, const __grid_constant__ CUtensorMa
         if (k < K - 1) __syncthreads();
         srcA = sa1; srcB = sb1;
     }
-    // ---- write the interior
+    // ---- write the interior (slabs: the first / last `depth` rows also go to the neighbours' halos)
+    const int rows_own = g.j1 - g.j0;
+    const bool plo = SLAB && A.push.peer[0][0] && by * TYO < A.push.depth;
+    const bool phi = SLAB && A.push.peer[1][0] && ((by + 1) * TYO < rows_own ? (by + 1) * TYO : rows_own) > rows_own - A.push.depth;
 #pragma unroll
     for (int v = 0; v < V; v++) {
         if (inmask & (1u << v)) {
-            const size_t n = g.at(x, yg0 + r0 + v);
+            const int y = yg0 + r0 + v;
+            const size_t n = g.at(x, y);
             ((R *)A.out_a)[n] = Av[v];
             ((R *)A.out_b)[n] = Bv[v];
+            if (plo && y < g.j0 + A.push.depth) {
+                const size_t m = (size_t)(y - A.push.peer_rb[0]) * g.P + x;
+                ((R *)A.push.peer[0][0])[m] = Av[v]; ((R *)A.push.peer[0][1])[m] = Bv[v];
+            }
+            if (phi && y >= g.j1 - A.push.depth) {
+                const size_t m = (size_t)(y - A.push.peer_rb[1]) * g.P + x;
+                ((R *)A.push.peer[1][0])[m] = Av[v]; ((R *)A.push.peer[1][1])[m] = Bv[v];
+            }
         }
     }
-    __syncthreads();
+    __syncthreads();                             // all peer stores of the CTA issued ...
+    if ((plo || phi) && tid == 0) {
+        __threadfence_system();                  // ... and made visible by ONE fence (grid-sync pattern)
+        for (int sdir = 0; sdir < 2; sdir++) {
+            if (!(sdir == 0 ? plo : phi)) continue;
+            unsigned int done = atomicAdd(&A.push.count[sdir], 1u);
+            if ((int)done == A.push_expect[sdir] - 1) {
+                A.push.count[sdir] = 0;
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.push.flag[sdir]), "l"(A.push.epoch) : "memory");
+            }
+        }
+    }
     if (tid < K) {
         unsigned long long b = sm_rmax[tid];
         if (b) atomicMax(A.slots + tid, b);
@@ -273,10 +305,12 @@ static int launch_a_tile_t(svl_ctx *c, ATileArgs &A, const void *psi, const void
     constexpr int H = sizeof(R) == 8 ? 2 : 4;
     constexpr int TX = TXE - 2 * H, TYO = S::EY - 2 * K;
     static_assert(S::guard >= (TXE + 1) * sizeof(R), "guard too small");
-    auto kern = k_a_tile<R, K, TXE, V, NB, MODE>;
+    auto kern = k_a_tile<R, K, TXE, V, NB, MODE, false>;
+    auto kern_slab = k_a_tile<R, K, TXE, V, NB, MODE, true>;       // with halo wait + in-kernel push
     static bool configured = false;
     if (!configured) {
         SVL_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total));
+        SVL_CHECK(cudaFuncSetAttribute(kern_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total));
         configured = true;
     }
     const bool dbl = sizeof(R) == 8;
@@ -287,8 +321,15 @@ static int launch_a_tile_t(svl_ctx *c, ATileArgs &A, const void *psi, const void
     SVL_TRY(svl_tma_map(&tm[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, psi, (size_t)g.Nx * cmul, g.rows, pc, TXE * cmul, S::EY));
     SVL_TRY(svl_tma_map(&tm[1], rt, a, g.Nx, g.rows, pr, TXE, S::EY));
     SVL_TRY(svl_tma_map(&tm[2], rt, b, g.Nx, g.rows, pr, TXE, S::EY));
-    int ntiles = ((g.Nx + TX - 1) / TX) * ((g.j1 - g.j0 + TYO - 1) / TYO);
-    kern<<<ntiles, TXE * NB, S::total, c->stream>>>(A, tm[0], tm[1], tm[2]);
+    const int ntx_ = (g.Nx + TX - 1) / TX, nty_ = (g.j1 - g.j0 + TYO - 1) / TYO, rows_ = g.j1 - g.j0;
+    A.push_expect[0] = A.push_expect[1] = 0;
+    for (int by = 0; by < nty_; by++) {
+        if (by * TYO < A.push.depth) A.push_expect[0] += ntx_;
+        if (((by + 1) * TYO < rows_ ? (by + 1) * TYO : rows_) > rows_ - A.push.depth) A.push_expect[1] += ntx_;
+    }
+    int ntiles = ntx_ * nty_;
+    if (A.wait_flags) kern_slab<<<ntiles, TXE * NB, S::total, c->stream>>>(A, tm[0], tm[1], tm[2]);
+    else kern<<<ntiles, TXE * NB, S::total, c->stream>>>(A, tm[0], tm[1], tm[2]);
     SVL_CHECK(cudaGetLastError());
     c->stat_launches += 1;
     return 0;
@@ -309,9 +350,10 @@ int svl_launch_a_tile(svl_ctx *c, int K, double dt, double kappa2, double rho, d
     A.nf = c->nf;
     A.out_a = out->p[0]; A.out_b = out->p[1];
     A.slots = resid_slots;
-    if (c->slab_on) {
+    if (c->slab_on && !c->opt_slab_nocomm) {
         A.wait_flags = c->flags; A.wait_epoch = svl_slab_epoch(c); A.has_lo = c->has_lo; A.has_hi = c->has_hi;
         svl_slab_mark_waited(c);
+        SVL_TRY(svl_slab_push_fused(c, out, &A.push));          // after wait_epoch: this launch's own push
     }
     const void *P_ = psi->p[0], *a_ = ab->p[0], *b_ = ab->p[1];
     // a_kernel option: 1 = 64x32 tile, 8 rows per thread, 2 CTAs/SM (default); 2 = same with the

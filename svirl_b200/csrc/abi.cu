@@ -75,6 +75,14 @@ extern "C" int svl_create(svl_ctx **out, int device_id, int Nx, int Ny, double d
     g.idx = 1.0 / dx; g.idy = 1.0 / dy;
     g.idx2 = 1.0 / (dx * dx); g.idy2 = 1.0 / (dy * dy); g.idxy = 1.0 / (dx * dy);
     SVL_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        SVL_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        SVL_CHECK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, hi));
+        SVL_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        SVL_CHECK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        SVL_CHECK(cudaEventCreateWithFlags(&c->ev_go, cudaEventDisableTiming));
+    }
     size_t nfb = (size_t)g.rows * g.P;
     SVL_CHECK(cudaMalloc(&c->nf, nfb));
     SVL_CHECK(cudaMalloc(&c->d_result, 64 * sizeof(double)));
@@ -91,6 +99,8 @@ extern "C" int svl_create(svl_ctx **out, int device_id, int Nx, int Ny, double d
     c->opt_graphs = 1;
     c->opt_a_kernel = 2;
     c->opt_cg_fused = 1;
+    c->opt_resid_board = 1;
+    c->opt_slab_split = 1;
     c->pred_psi = c->pred_A = c->pred_psi2 = c->pred_A2 = 0;
     *out = c;
     return svl_set_material(c, nullptr);
@@ -105,11 +115,14 @@ extern "C" int svl_destroy(svl_ctx *c) {
         if (c->ab_s[k]) svl_free(c, c->ab_s[k]);
     }
     cudaFree(c->arena);
+    cudaFree(c->board);
     cudaFree(c->nf); cudaFree(c->d_result); cudaFreeHost(c->h_result);
     cudaFree(c->d_resid); cudaFreeHost(c->h_resid); cudaFree(c->d_counter);
     cudaFree(c->partials); cudaFree(c->d_cand); cudaFree(c->d_candv); cudaFree(c->d_ncand);
     for (int k = 0; k < 8; k++) cudaEventDestroy(c->ev[k]);
     cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->stream2);
+    cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); cudaEventDestroy(c->ev_go);
     delete c;
     return 0;
 }
@@ -145,6 +158,20 @@ extern "C" int svl_set_option(svl_ctx *c, const char *name, int v) {
     else if (!strcmp(name, "graphs")) c->opt_graphs = v;
     else if (!strcmp(name, "a_kernel")) c->opt_a_kernel = v;
     else if (!strcmp(name, "cg_fused")) c->opt_cg_fused = v;
+    else if (!strcmp(name, "resid_board")) c->opt_resid_board = v;
+    else if (!strcmp(name, "slab_split")) c->opt_slab_split = v;
+    else if (!strcmp(name, "slab_nocomm")) c->opt_slab_nocomm = v;     // timing experiments only: ranks run uncoupled
+    else if (!strcmp(name, "trace")) {                                 // diagnostics: record v launches from now on
+        SVL_CHECK(cudaStreamSynchronize(c->stream));
+        cudaFree(c->trace); c->trace = nullptr; c->trace_n = c->trace_cap = 0;
+        if (v > 0) {
+            std::vector<unsigned long long> init((size_t)4 * v, 0ull);
+            for (int k = 0; k < v; k++) init[4 * k] = ~0ull;
+            SVL_CHECK(cudaMalloc(&c->trace, init.size() * sizeof(unsigned long long)));
+            SVL_CHECK(cudaMemcpy(c->trace, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+            c->trace_cap = v;
+        }
+    }
     else if (!strcmp(name, "reset_prediction")) { c->pred_psi = c->pred_A = c->pred_psi2 = c->pred_A2 = 0; }
     else { svl_set_error("unknown option %s", name); return 2; }
     return 0;
@@ -366,5 +393,15 @@ extern "C" int svl_debug_sincos(svl_ctx *c, size_t n, const double *x, double *s
     SVL_CHECK(cudaMemcpyAsync(c_out, d + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     SVL_CHECK(cudaStreamSynchronize(c->stream));
     cudaFree(d);
+    return 0;
+}
+
+// diagnostics: copy the per-launch trace records (4 words each) to the host; returns the count through n_out
+extern "C" int svl_debug_trace(svl_ctx *c, unsigned long long *out, int max_records, int *n_out) {
+    SVL_REQUIRE(c && out && n_out, "null argument");
+    SVL_CHECK(cudaStreamSynchronize(c->stream));
+    int n = c->trace_n < max_records ? c->trace_n : max_records;
+    if (n > 0) SVL_CHECK(cudaMemcpy(out, c->trace, (size_t)4 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    *n_out = n;
     return 0;
 }

@@ -11,6 +11,7 @@
 
 #define SVL_HALO 8            // halo rows kept above/below the owned rows of every plane (>= max fused sweeps)
 #define SVL_MAX_SWEEPS 1024   // svirl/solvers/td.py:164, 274
+#define SVL_MAX_RANKS 16      // GPUs of one NVLink box that can share a residual board
 
 // ----------------------------------------------------------------------------- errors
 void svl_set_error(const char *fmt, ...);
@@ -75,6 +76,8 @@ struct svl_ctx {
     int rsize;                     // 4 or 8
     Geo g;
     cudaStream_t stream;
+    cudaStream_t stream2;          // slabs: boundary-tile launches (high priority), forked from / joined to `stream`
+    cudaEvent_t ev_fork, ev_join, ev_go;
     // per-node material flags (always present)
     uint8_t *nf;
     bool have_mt;
@@ -92,7 +95,7 @@ struct svl_ctx {
     // vortex candidates
     long long *d_cand; double *d_candv; unsigned long long *d_ncand; size_t cand_cap;
     // options / stats
-    int opt_psi_kernel, opt_psi_k, opt_tma, opt_graphs, opt_a_kernel, opt_cg_fused;
+    int opt_psi_kernel, opt_psi_k, opt_tma, opt_graphs, opt_a_kernel, opt_cg_fused, opt_resid_board, opt_slab_nocomm, opt_slab_split;
     int pred_psi, pred_A;          // sweep counts of the previous solve
     int pred_psi2, pred_A2;        // ... and of the one before (trend)
     double stat_launches, stat_replays, stat_psi_sweeps, stat_A_sweeps;
@@ -113,6 +116,14 @@ struct svl_ctx {
     void (*reduce_max_u64)(unsigned long long *vals, int n);      // host values
     void (*reduce_max_dev)(unsigned long long *dvals, int n);     // device values, enqueued on c->stream
     unsigned int *push_count;      // [2] completion counters of the push kernel
+    // residual board: every rank's per-sweep slots, written by the owners with peer stores (slab.cu)
+    unsigned long long *board;           // own board (separate allocation, own IPC handle)
+    unsigned long long *board_peer[SVL_MAX_RANKS];   // everybody's board, [rank] = own
+    int board_rank, board_world;         // world == 0: not connected
+    unsigned long long board_epoch;
+    // diagnostics: per-launch timestamps of the slab tile kernels (option "trace" = number of launches)
+    unsigned long long *trace;
+    int trace_n, trace_cap;
 };
 
 static inline int svl_nblocks(size_t n, int b) { return (int)((n + b - 1) / b); }
@@ -131,6 +142,18 @@ int svl_finish_sum(svl_ctx *c, int nblocks, int nv, double scale, double *out_ho
 int svl_slab_push_psi(svl_ctx *c, const svl_buf *buf);       // boundary rows of a psi buffer -> neighbours' halos
 int svl_slab_push_ab(svl_ctx *c, const svl_buf *buf);
 int svl_slab_wait(svl_ctx *c);                               // wait until all pushes so far have arrived
+int svl_board_allmax(svl_ctx *c, int first, int count);      // d_resid[first..] <- MAX over ranks (peer memory)
+// In-kernel push (tile kernels): the tiles that own the first / last `depth` rows store their results
+// into the neighbours' halo rows as well and the last of them publishes the epoch.
+struct SlabPush {
+    void *peer[2][2];              // [direction lo/hi][plane]: neighbour's copy of the output plane(s), or null
+    int peer_rb[2];                // rb of that neighbour (its plane row 0 is global row peer_rb)
+    unsigned long long *flag[2];   // neighbour's epoch word for this direction
+    unsigned long long epoch;      // value to publish
+    unsigned int *count;           // [2] completion counters (self-resetting)
+    int depth;                     // rows pushed on each side
+};
+int svl_slab_push_fused(svl_ctx *c, const svl_buf *out, SlabPush *info);   // accounts the push, fills info
 unsigned long long svl_slab_epoch(svl_ctx *c);               // pushes issued so far (what a consumer must wait for)
 void svl_slab_mark_waited(svl_ctx *c);                       // the next kernel waits by itself
 // abi.cu

@@ -29,6 +29,12 @@ struct TileArgs {
     const unsigned long long *wait_flags;
     unsigned long long wait_epoch;
     int has_lo, has_hi;
+    SlabPush push;                 // slabs: in-kernel push of the output's boundary rows
+    int push_expect[2];            // tiles that contribute to the lo / hi push
+    int row0, nrow, row1, nrow1;   // tile rows this launch covers: [row0, row0+nrow) then [row1, row1+nrow1)
+    int permute;                   // slabs, single launch: process the first / last tile row last
+    unsigned long long *trace;     // slabs, diagnostics: [0] first CTA start, [1] last CTA end, [2] longest flag wait,
+                                   // [3] time the last flag wait ended (all %globaltimer ns), or null
 };
 
 __device__ __forceinline__ uint32_t t_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -67,7 +73,7 @@ struct TileSmem {
 // Persistent CTAs: each loops over tiles tile = blockIdx.x, +gridDim.x, ...; the TMA boxes of the
 // next tile are issued as soon as this tile's constants are in registers, so the load overlaps the
 // K sweeps.
-template <typename R, int K, int TXE, int V, int NB, bool EPS>
+template <typename R, int K, int TXE, int V, int NB, bool EPS, bool SLAB>
 __global__ void __launch_bounds__(TXE *NB, (sizeof(R) == 4 ? 2 : 1))
 k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorMap tm_psi,
            const __grid_constant__ CUtensorMap tm_rhs, const __grid_constant__ CUtensorMap tm_a,
@@ -88,12 +94,41 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
     const int col = tid % TXE, band = tid / TXE;
     const int r0 = band * V;                             // first tile row of this thread
     const int ntx = (g.Nx + TX - 1) / TX, nty = (g.j1 - g.j0 + TYO - 1) / TYO;
-    const int ntiles = ntx * nty;
+    const int ntiles = (SLAB && A.permute) ? ntx * nty : ntx * (A.nrow + A.nrow1);
     const R dt = (R)A.dt, dx = (R)g.dx, dy = (R)g.dy, idx2 = (R)g.idx2, idy2 = (R)g.idy2;
     const R cx = dt * idx2, cy = dt * idy2, eps0 = (R)A.eps, lang = (R)A.lang_c;
 
-    auto issue = [&](int tile) {                         // thread 0 only
+    // Tile rows of this launch: [row0, row0+nrow) then [row1, row1+nrow1).  Slabs, single launch
+    // (permute): those two ranges are the boundary rows (they read a neighbour's halo rows and feed the
+    // push) and are processed FIRST -- the neighbour's previous push landed a whole launch ago, so
+    // the flag wait is free, and this launch's push leaves early -- followed by the interior rows.
+    auto tile_of = [&](int q) {
+        const int r = q / ntx, nb = A.nrow + A.nrow1;
+        int by = r < A.nrow ? A.row0 + r : A.row1 + (r - A.nrow);
+        if (SLAB && A.permute && r >= nb) by = A.nrow + (r - nb);        // interior rows [nrow, nty - nrow1)
+        return by * ntx + q % ntx;
+    };
+    bool flags_seen[2] = {false, false};                 // thread 0 only
+    auto gtime = [&]() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    auto wait_side = [&](int sdir) {
+        if (flags_seen[sdir] || !(sdir == 0 ? A.has_lo : A.has_hi)) return;
+        unsigned long long v = 0;
+        long long t0 = clock64();
+        const unsigned long long g0 = A.trace ? gtime() : 0ull;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(A.wait_flags + sdir) : "memory");
+            if (clock64() - t0 > 20000000000ll) __trap();
+        } while (v < A.wait_epoch);
+        if (A.trace) { const unsigned long long g1 = gtime(); atomicMax(A.trace + 2, g1 - g0); atomicMax(A.trace + 3, g1); }
+        flags_seen[sdir] = true;
+    };
+    auto issue = [&](int q) {                            // thread 0 only
+        const int tile = tile_of(q);
         const int bx = tile % ntx, by = tile / ntx;
+        if (SLAB) {
+            if (by == 0) wait_side(0);
+            if (by == nty - 1) wait_side(1);
+        }
         const int xg0 = bx * TX - H, prow = g.j0 + by * TYO - K - g.rb;
         const int xs16 = ((xg0 + 1024) / 16) * 16 - 1024;
         uint32_t bytes = S::tx_bytes;
@@ -109,21 +144,11 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
     };
 
     int tile = blockIdx.x;
+    if (SLAB && A.trace && tid == 0) atomicMin(A.trace + 0, gtime());
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(t_smem_u32(bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (A.wait_flags) {
-            for (int sdir = 0; sdir < 2; sdir++) {
-                if (!(sdir == 0 ? A.has_lo : A.has_hi)) continue;
-                unsigned long long v = 0;
-                long long t0 = clock64();
-                do {
-                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(A.wait_flags + sdir) : "memory");
-                    if (clock64() - t0 > 20000000000ll) __trap();
-                } while (v < A.wait_epoch);
-            }
-        }
         if (tile < ntiles) issue(tile);
     }
     // zero the pad ring of the exchange / coefficient tiles once (never overwritten afterwards)
@@ -143,8 +168,9 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
     if (tid < K) { sm_rmax[tid] = 0u; sm_rmax64[tid] = 0ull; }
     uint32_t phase = 0;
 
-    for (; tile < ntiles; tile += gridDim.x) {
-        const int bx = tile % ntx, by = tile / ntx;
+    for (; tile < ntiles; tile += gridDim.x) {           // `tile` counts positions in the processing order
+        const int tcur = tile_of(tile);
+        const int bx = tcur % ntx, by = tcur / ntx;
         const int xg0 = bx * TX - H;                     // global column of tile column 0
         const int yg0 = g.j0 + by * TYO - K;             // global row of tile row 0
         const int x = xg0 + col;
@@ -261,12 +287,36 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
             if (k < K - 1) __syncthreads();
             const C *tsw = src; src = dst; dst = (C *)tsw;
         }
-        // ---- write the interior
+        // ---- write the interior (slabs: the first / last `depth` rows also go to the neighbours' halos)
+        const int rows_own = g.j1 - g.j0;
+        const bool plo = SLAB && A.push.peer[0][0] && by * TYO < A.push.depth;
+        const bool phi = SLAB && A.push.peer[1][0] && ((by + 1) * TYO < rows_own ? (by + 1) * TYO : rows_own) > rows_own - A.push.depth;
 #pragma unroll
         for (int v = 0; v < V; v++) {
-            if (inmask & (1u << v)) ((C *)A.out)[g.at(x, yg0 + r0 + v)] = psi[v];
+            if (inmask & (1u << v)) {
+                const int y = yg0 + r0 + v;
+                ((C *)A.out)[g.at(x, y)] = psi[v];
+                if (plo && y < g.j0 + A.push.depth) ((C *)A.push.peer[0][0])[(size_t)(y - A.push.peer_rb[0]) * g.P + x] = psi[v];
+                if (phi && y >= g.j1 - A.push.depth) ((C *)A.push.peer[1][0])[(size_t)(y - A.push.peer_rb[1]) * g.P + x] = psi[v];
+            }
+        }
+        if (plo || phi) {                        // CTA-uniform
+            __syncthreads();                     // all peer stores of the CTA issued ...
+            if (tid == 0) {
+                __threadfence_system();          // ... and made visible by ONE fence (grid-sync pattern)
+                for (int sdir = 0; sdir < 2; sdir++) {
+                    if (!(sdir == 0 ? plo : phi)) continue;
+                    unsigned int done = atomicAdd(&A.push.count[sdir], 1u);
+                    if ((int)done == A.push_expect[sdir] - 1) {
+                        A.push.count[sdir] = 0;
+                        __threadfence_system();
+                        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.push.flag[sdir]), "l"(A.push.epoch) : "memory");
+                    }
+                }
+            }
         }
     }
+    if (SLAB && A.trace && tid == 0) atomicMax(A.trace + 1, gtime());
     // ---- per-sweep max-norm updates -> one global atomicMax per CTA and sweep
     __syncthreads();
     if (tid < K) {
@@ -340,12 +390,14 @@ static int launch_tile_t(svl_ctx *c, TileArgs &A, const TileIO &io) {
     const Geo &g = c->g;
     constexpr int TX = TXE - 2 * S::H, TYO = S::EY - 2 * K;
     static_assert(TYO > 0 && TX > 0, "tile too small for this K");
-    auto kern = k_psi_tile<R, K, TXE, V, NB, EPS>;
+    auto kern = k_psi_tile<R, K, TXE, V, NB, EPS, false>;
+    auto kern_slab = k_psi_tile<R, K, TXE, V, NB, EPS, true>;       // with halo wait + in-kernel push
     static int slots = 0;
     if (!slots) {
         int occ = 1, nsm = 148;
         SVL_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total));
-        SVL_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TXE * NB, S::total));
+        SVL_CHECK(cudaFuncSetAttribute(kern_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total));
+        SVL_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern_slab, TXE * NB, S::total));
         SVL_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
         slots = (occ < 1 ? 1 : occ) * nsm;
     }
@@ -362,9 +414,48 @@ static int launch_tile_t(svl_ctx *c, TileArgs &A, const TileIO &io) {
     SVL_TRY(svl_tma_map(&tm[3], rt, io.b, g.Nx, g.rows, pr, TXE, S::EY));
     SVL_TRY(svl_tma_map(&tm[4], rt, EPS ? io.epsf : io.a, g.Nx, g.rows, pr, TXE, S::EY));
     SVL_TRY(svl_tma_map(&tm[5], CU_TENSOR_MAP_DATA_TYPE_UINT8, io.nf, g.Nx, g.rows, (size_t)g.P, S::NFW, S::EY));
-    int ntiles = ((g.Nx + TX - 1) / TX) * ((g.j1 - g.j0 + TYO - 1) / TYO);
-    int grid = ntiles < slots ? ntiles : slots;
-    kern<<<grid, TXE * NB, S::total, c->stream>>>(A, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]);
+    const int ntx_ = (g.Nx + TX - 1) / TX, nty_ = (g.j1 - g.j0 + TYO - 1) / TYO, rows_ = g.j1 - g.j0;
+    A.push_expect[0] = A.push_expect[1] = 0;
+    int nlo = 0, nhi = 0;                                  // tile rows that feed the lo / hi push
+    for (int by = 0; by < nty_; by++) {
+        if (by * TYO < A.push.depth) { A.push_expect[0] += ntx_; if (A.push.peer[0][0]) nlo++; }
+        if (((by + 1) * TYO < rows_ ? (by + 1) * TYO : rows_) > rows_ - A.push.depth) { A.push_expect[1] += ntx_; if (A.push.peer[1][0]) nhi++; }
+    }
+    A.row0 = 0; A.nrow = nty_; A.row1 = 0; A.nrow1 = 0; A.permute = 0;
+    if (!A.wait_flags) {
+        int ntiles = ntx_ * nty_;
+        kern<<<ntiles < slots ? ntiles : slots, TXE * NB, S::total, c->stream>>>(A, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]);
+    } else if (c->opt_slab_split && nty_ - nlo - nhi > 0 && nlo + nhi > 0) {
+        // Slabs, two launches per batch: the boundary tile rows (halo wait + in-kernel push) on a
+        // high-priority side stream, the interior rows with the plain kernel on the main stream;
+        // both read `cur` and write disjoint rows of `out`.  The pushes leave early in the batch.
+        SVL_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+        SVL_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+        // the interior launch is released through the side stream ("go"), a moment after the boundary
+        // launch became runnable: the persistent interior CTAs would otherwise take every SM slot first
+        SVL_CHECK(cudaEventRecord(c->ev_go, c->stream2));
+        TileArgs B = A;
+        B.row0 = 0; B.nrow = nlo; B.row1 = nty_ - nhi; B.nrow1 = nhi;
+        int nb = ntx_ * (nlo + nhi);
+        kern_slab<<<nb < slots ? nb : slots, TXE * NB, S::total, c->stream2>>>(B, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]);
+        SVL_CHECK(cudaGetLastError());
+        SVL_CHECK(cudaEventRecord(c->ev_join, c->stream2));
+        TileArgs I = A;
+        I.wait_flags = nullptr; memset(&I.push, 0, sizeof(I.push)); I.trace = nullptr;
+        I.row0 = nlo; I.nrow = nty_ - nlo - nhi;
+        int ni = ntx_ * I.nrow;
+        SVL_CHECK(cudaStreamWaitEvent(c->stream, c->ev_go, 0));
+        kern<<<ni < slots ? ni : slots, TXE * NB, S::total, c->stream>>>(I, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]);
+        SVL_CHECK(cudaGetLastError());
+        SVL_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        c->stat_launches += 1;
+    } else {
+        A.permute = 1;                                   // boundary rows first, then the interior
+        A.row0 = 0; A.nrow = nlo; A.row1 = nty_ - nhi; A.nrow1 = nhi;
+        if (nty_ - nlo - nhi < 0) { A.permute = 0; A.row0 = 0; A.nrow = nty_; A.row1 = 0; A.nrow1 = 0; }
+        int ntiles = ntx_ * nty_;
+        kern_slab<<<ntiles < slots ? ntiles : slots, TXE * NB, S::total, c->stream>>>(A, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]);
+    }
     SVL_CHECK(cudaGetLastError());
     c->stat_launches += 1;
     return 0;
@@ -394,9 +485,14 @@ int svl_launch_psi_tile(svl_ctx *c, int K, double dt, double eps, const svl_buf 
     A.noise = lang_c > 1.0e-32 ? 1 : 0;
     A.same_rhs = rhs->p[0] == psi->p[0];
     A.out = out->p[0]; A.slots = resid_slots;
-    if (c->slab_on) {
+    if (c->slab_on && !c->opt_slab_nocomm) {
         A.wait_flags = c->flags; A.wait_epoch = svl_slab_epoch(c); A.has_lo = c->has_lo; A.has_hi = c->has_hi;
         svl_slab_mark_waited(c);
+        SVL_TRY(svl_slab_push_fused(c, out, &A.push));          // after wait_epoch: this launch's own push
+        if (c->trace && c->trace_n < c->trace_cap) {
+            A.trace = c->trace + 4 * (size_t)c->trace_n;
+            c->trace_n += 1;
+        }
     }
     TileIO io = {psi->p[0], rhs->p[0], ab->p[0], ab->p[1], epsf ? epsf->p[0] : nullptr, c->nf};
     if (c->rsize == 4) {

@@ -118,11 +118,34 @@ int svl_slab_push_ab(svl_ctx *c, const svl_buf *buf) {
     return push_planes(c, pl, 2, buf->esize, c->epoch_psi + c->epoch_A);
 }
 
+// The push of `out` will be done by the kernel that writes it: count it and describe the targets.
+int svl_slab_push_fused(svl_ctx *c, const svl_buf *out, SlabPush *info) {
+    memset(info, 0, sizeof(*info));
+    if (!c->slab_on) return 0;
+    const int nplanes = out->kind == SVL_EDGE ? 2 : 1;
+    if (out->kind == SVL_EDGE) c->epoch_A += 1; else c->epoch_psi += 1;
+    const Geo &g = c->g;
+    int rows = g.j1 - g.j0;
+    info->depth = SVL_HALO < rows ? SVL_HALO : rows;
+    info->epoch = c->epoch_psi + c->epoch_A;
+    info->count = c->push_count;
+    for (int q = 0; q < nplanes; q++) {
+        int id = phys_of(c, out->p[q]);
+        SVL_REQUIRE(id >= 0, "slab push: buffer is not one of the registered planes");
+        if (c->has_lo) info->peer[0][q] = c->peer[0][id];
+        if (c->has_hi) info->peer[1][q] = c->peer[1][id];
+    }
+    info->peer_rb[0] = c->nb_rb[0]; info->peer_rb[1] = c->nb_rb[1];
+    if (c->has_lo) info->flag[0] = c->peer_flags[0] + 1;      // I am the lower neighbour's "hi"
+    if (c->has_hi) info->flag[1] = c->peer_flags[1] + 0;
+    return 0;
+}
+
 unsigned long long svl_slab_epoch(svl_ctx *c) { return c->epoch_psi + c->epoch_A; }
 void svl_slab_mark_waited(svl_ctx *c) { c->waited = c->epoch_psi + c->epoch_A; }
 
 int svl_slab_wait(svl_ctx *c) {
-    if (!c->slab_on) return 0;
+    if (!c->slab_on || c->opt_slab_nocomm) return 0;
     unsigned long long e = c->epoch_psi + c->epoch_A;
     if (e == c->waited) return 0;
     k_wait_flags<<<1, 1, 0, c->stream>>>(c->flags, c->has_lo, c->has_hi, e);
@@ -216,5 +239,91 @@ extern "C" int svl_slab_exchange(svl_ctx *c, svl_buf *buf) {
     else { svl_set_error("slab exchange: only psi / ab buffers are registered"); return 2; }
     SVL_TRY(svl_slab_wait(c));
     SVL_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- residual board
+// MAX of the per-sweep residual slots over all ranks without NCCL or the host: every rank writes
+// its slots into every rank's board with peer stores, publishes an epoch word per destination, waits
+// until all ranks' epochs have arrived on its own board and takes the maximum.  One small kernel
+// per read-back (NVLink write latency + polling, a few microseconds) instead of an NCCL all-reduce
+// driven from a Python callback.  Boards are double buffered by epoch parity: a rank cannot be two
+// exchanges ahead of another one, because each exchange waits for everybody's epoch.
+#define BOARD_WORDS (2 * SVL_MAX_RANKS * SVL_MAX_SWEEPS)      // slots[parity][rank][sweep], then epochs[rank]
+
+struct BoardArgs {
+    unsigned long long *peer[SVL_MAX_RANKS];
+    int rank, world;
+};
+
+__global__ void __launch_bounds__(256)
+k_board_allmax(BoardArgs B, unsigned long long *d_resid, int first, int count, unsigned long long epoch) {
+    const int par = (int)(epoch & 1ull);
+    const size_t mine = ((size_t)(par * SVL_MAX_RANKS + B.rank)) * SVL_MAX_SWEEPS + first;
+    for (int r = 0; r < B.world; r++) {
+        unsigned long long *dst = B.peer[r] + mine;
+        for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = d_resid[first + i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < B.world) {
+        unsigned long long *e = B.peer[threadIdx.x] + BOARD_WORDS + B.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(e), "l"(epoch) : "memory");
+        const unsigned long long *w = B.peer[B.rank] + BOARD_WORDS + threadIdx.x;
+        unsigned long long v = 0;
+        long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
+            if (clock64() - t0 > 20000000000ll) __trap();      // ~10 s: a rank died
+        } while (v < epoch);
+    }
+    __syncthreads();
+    const unsigned long long *own = B.peer[B.rank] + (size_t)par * SVL_MAX_RANKS * SVL_MAX_SWEEPS + first;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        unsigned long long m = 0;
+        for (int r = 0; r < B.world; r++) {
+            unsigned long long v = __ldcv(own + (size_t)r * SVL_MAX_SWEEPS + i);     // written by peers: bypass L1
+            m = v > m ? v : m;
+        }
+        d_resid[first + i] = m;
+    }
+}
+
+int svl_board_allmax(svl_ctx *c, int first, int count) {
+    BoardArgs B;
+    memset(&B, 0, sizeof(B));
+    for (int r = 0; r < c->board_world; r++) B.peer[r] = c->board_peer[r];
+    B.rank = c->board_rank; B.world = c->board_world;
+    c->board_epoch += 1;
+    k_board_allmax<<<1, 256, 0, c->stream>>>(B, c->d_resid, first, count, c->board_epoch);
+    SVL_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int svl_slab_board_export(svl_ctx *c, void *handle_out) {
+    SVL_REQUIRE(c && handle_out, "null argument");
+    SVL_REQUIRE(!c->board, "residual board already exported");
+    size_t bytes = (size_t)(BOARD_WORDS + SVL_MAX_RANKS) * sizeof(unsigned long long);
+    // a separate allocation of >= 2 MB gets its own driver allocation, hence its own IPC handle
+    if (bytes < (4u << 20)) bytes = 4u << 20;
+    SVL_CHECK(cudaMalloc(&c->board, bytes));
+    SVL_CHECK(cudaMemset(c->board, 0, bytes));
+    SVL_CHECK(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle_out, c->board));
+    SVL_CHECK(cudaDeviceSynchronize());
+    return 0;
+}
+
+// handles: world x 64 bytes in rank order (this rank's own entry is ignored)
+extern "C" int svl_slab_board_connect(svl_ctx *c, int rank, int world, const void *handles) {
+    SVL_REQUIRE(c && handles && c->board, "export the board first");
+    SVL_REQUIRE(world >= 1 && world <= SVL_MAX_RANKS && rank >= 0 && rank < world, "bad rank/world");
+    const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)handles;
+    for (int r = 0; r < world; r++) {
+        if (r == rank) { c->board_peer[r] = c->board; continue; }
+        void *p = nullptr;
+        SVL_CHECK(cudaIpcOpenMemHandle(&p, h[r], cudaIpcMemLazyEnablePeerAccess));
+        c->board_peer[r] = (unsigned long long *)p;
+    }
+    c->board_rank = rank; c->board_world = world; c->board_epoch = 0;
     return 0;
 }

@@ -221,11 +221,13 @@ static inline double slot_value(unsigned long long bits) {
 
 static int read_resid(svl_ctx *c, int first, int count) {
     // slabs: MAX over ranks (bit patterns of non-negative doubles order like integers; exact)
-    if (c->reduce_max_dev) c->reduce_max_dev(c->d_resid + first, count);      // enqueued on c->stream
+    const bool board = c->board_world > 1 && c->opt_resid_board && !c->opt_slab_nocomm;
+    if (board) SVL_TRY(svl_board_allmax(c, first, count));                    // peer memory, no host, no NCCL
+    else if (c->reduce_max_dev && !c->opt_slab_nocomm) c->reduce_max_dev(c->d_resid + first, count); // NCCL, enqueued on c->stream
     SVL_CHECK(cudaMemcpyAsync(c->h_resid + first, c->d_resid + first, (size_t)count * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, c->stream));
     SVL_CHECK(cudaStreamSynchronize(c->stream));
-    if (c->reduce_max_u64 && !c->reduce_max_dev) c->reduce_max_u64(c->h_resid + first, count);
+    if (!board && c->reduce_max_u64 && !c->reduce_max_dev) c->reduce_max_u64(c->h_resid + first, count);
     return 0;
 }
 
@@ -323,16 +325,19 @@ static int psi_launch_range(svl_ctx *c, const PsiSolveArgs &A, PsiIter &it, int 
             else K = want >= 4 ? 4 : 0;              // plain-load staging is built for K = 4 only
         }
         svl_buf *out = it.S[it.toggle];
-        SVL_TRY(svl_slab_wait(c));                   // neighbours' halo rows of the input have arrived
+        bool pushed = false;                         // the tile kernel waits for its halos and pushes its own
         if (K > 0 && c->opt_psi_kernel == 2) {
             SVL_TRY(svl_launch_psi_tile(c, K, A.dt, A.eps, A.epsf, A.ab, it.B0, it.cur, out, A.lang_c, A.rand_t, c->d_resid + s));
+            pushed = true;
         } else if (K > 0) {
+            SVL_TRY(svl_slab_wait(c));               // neighbours' halo rows of the input have arrived
             SVL_TRY(svl_launch_psi_stream(c, K, A.dt, A.eps, A.epsf, A.ab, it.B0, it.cur, out, A.lang_c, A.rand_t, c->d_resid + s));
         } else {
             K = 1;
+            SVL_TRY(svl_slab_wait(c));
             SVL_TRY(svl_launch_psi_sweep(c, A.dt, A.eps, A.epsf, A.ab, it.B0, it.cur, out, A.lang_c, A.rand_t, c->d_resid + s));
         }
-        SVL_TRY(svl_slab_push_psi(c, out));          // my boundary rows -> neighbours' halos (peer stores)
+        if (!pushed) SVL_TRY(svl_slab_push_psi(c, out));   // my boundary rows -> neighbours' halos (peer stores)
         it.prev = it.cur; it.cur = out; it.toggle ^= 1; it.lastK = K;
         s += K;
     }
@@ -419,12 +424,14 @@ static int a_advance(svl_ctx *c, const ASolveArgs &A, AIter &it, int upto) {
         it.l_s = it.s; it.l_cur = it.cur; it.l_even = it.even;
         int K = 1;
         svl_buf *out;
+        bool pushed = false;                         // the tile kernel waits for its halos and pushes its own
         if ((it.s & 1) == 0) {
             out = it.cur == it.S1 ? it.S2 : it.S1;
             if (c->opt_a_kernel >= 1) {
                 K = upto - it.s >= 2 ? 2 : 1;
                 SVL_TRY(svl_launch_a_tile(c, K, A.dt, A.kappa2, A.rho, A.H, A.psi, it.B0, it.cur, out, A.lang_c, A.rand_t,
                                           c->d_resid + it.s));
+                pushed = true;
             } else {
                 SVL_TRY(svl_slab_wait(c));
                 SVL_TRY(svl_launch_a_sweep(c, A.dt, A.kappa2, A.rho, A.H, A.psi, it.cur, it.B0, it.cur, out, A.lang_c,
@@ -439,7 +446,7 @@ static int a_advance(svl_ctx *c, const ASolveArgs &A, AIter &it, int upto) {
                                        noise, c->d_resid + it.s));
             it.cur = it.even = out;
         }
-        SVL_TRY(svl_slab_push_ab(c, out));
+        if (!pushed) SVL_TRY(svl_slab_push_ab(c, out));
         it.s += K; it.l_K = K;
     }
     return 0;

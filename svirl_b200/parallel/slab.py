@@ -60,6 +60,15 @@ class SlabComm(object):
                   C.cast(self._keep[0], C.c_void_p) if lo else None, lo[1][0] if lo else 0,
                   C.cast(self._keep[1], C.c_void_p) if hi else None, hi[1][0] if hi else 0)
 
+        # residual board: all-to-all peer memory for the MAX of the residual slots (NVLink, no NCCL)
+        if dist.get_backend(group) == "nccl" and self.world <= 16:
+            bh = (C.c_char * 64)()
+            _lib.call("svl_slab_board_export", par.ctx, C.cast(bh, C.c_void_p))
+            allh = [None] * self.world
+            dist.all_gather_object(allh, bytes(bh), group=group)
+            self._board_handles = C.create_string_buffer(b"".join(allh), 64 * self.world)
+            _lib.call("svl_slab_board_connect", par.ctx, self.rank, self.world, C.cast(self._board_handles, C.c_void_p))
+
         @C.CFUNCTYPE(None, C.POINTER(C.c_ulonglong), C.c_int)
         def _reduce(ptr, n):
             arr = np.ctypeslib.as_array(ptr, shape=(n,))
