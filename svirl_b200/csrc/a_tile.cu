@@ -103,7 +103,8 @@ k_a_tile(const __grid_constant__ ATileArgs A, const __grid_constant__ CUtensorMa
         if (SLAB) {                                        // slabs: the neighbours' halo rows of the input have arrived
             for (int sdir = 0; sdir < 2; sdir++) {
                 if (!(sdir == 0 ? A.has_lo : A.has_hi)) continue;
-                if (by != (sdir == 0 ? 0 : nty - 1)) continue;          // interior tile: nothing to wait for
+                const int rows_own = g.j1 - g.j0, top = (by + 1) * TYO < rows_own ? (by + 1) * TYO : rows_own;
+                if (sdir == 0 ? (by * TYO - K >= 0) : (top + K <= rows_own)) continue;   // box stays inside the slab
                 unsigned long long v = 0;
                 long long t0 = clock64();
                 do {

@@ -125,9 +125,10 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
     auto issue = [&](int q) {                            // thread 0 only
         const int tile = tile_of(q);
         const int bx = tile % ntx, by = tile / ntx;
-        if (SLAB) {
-            if (by == 0) wait_side(0);
-            if (by == nty - 1) wait_side(1);
+        if (SLAB) {      // tile rows whose input box reaches into a neighbour's halo rows (K rows beyond the tile)
+            const int rows_own = g.j1 - g.j0, top = (by + 1) * TYO < rows_own ? (by + 1) * TYO : rows_own;
+            if (by * TYO - K < 0) wait_side(0);
+            if (top + K > rows_own) wait_side(1);
         }
         const int xg0 = bx * TX - H, prow = g.j0 + by * TYO - K - g.rb;
         const int xs16 = ((xg0 + 1024) / 16) * 16 - 1024;

@@ -29,7 +29,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    Nx, Ny = 300, 401
+    Nx, Ny = 300, int(os.environ.get("SLAB_NY", "401"))      # SLAB_NY=201 on 4 ranks: 50-row slabs (edge case)
     rs = np.random.RandomState(3)
     mt = rs.rand(Nx - 1, Ny - 1) > 0.1
     ok = True
