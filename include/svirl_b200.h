@@ -109,6 +109,16 @@ int svl_td_psi_solve(svl_ctx *ctx, double dt, double eps, const svl_buf *eps_fie
 /* Whole A-solve (svirl/solvers/td.py:252-325) including the link-phase aliasing quirk Q1. */
 int svl_td_a_solve(svl_ctx *ctx, double dt, double kappa2, double rho, double H, const svl_buf *psi,
                    svl_buf *ab, double langevin_c, uint32_t rand_t, double stop_eps, int *sweeps_out);
+/* Fixed vortices (svirl/vars/fixed_vortices.py, svirl/solvers/td.py:120-155, 207-216, 257-266, 319-325):
+ *  svl_td_a_solve_ph  A-solve whose link phase comes from a separate, unperturbed buffer in every sweep;
+ *  svl_edge_axpy_flat x[0:n_flat] += sign * y[0:n_flat] in the reference's packed edge order (xpy_r / xmy_r
+ *                     launched with N = Nx*Ny on Na+Nb entries: quirk Q5, reproduced);
+ *  svl_phase_lock     psi[n] <- |psi[n]| on a list of flat node indices (order_parameter_phase_lock). */
+int svl_td_a_solve_ph(svl_ctx *ctx, double dt, double kappa2, double rho, double H, const svl_buf *psi,
+                      const svl_buf *ab_phase, svl_buf *ab, double langevin_c, uint32_t rand_t, double stop_eps,
+                      int *sweeps_out);
+int svl_edge_axpy_flat(svl_ctx *ctx, svl_buf *x, const svl_buf *y, double sign, long long n_flat);
+int svl_phase_lock(svl_ctx *ctx, svl_buf *psi, const svl_buf *lock_ns, int count);
 /* Nt time steps of [psi-solve; A-solve if solveA] (svirl/solvers/td.py:342-367); rand_t is
  * incremented after every solve and returned.  sweeps[0..1] accumulate psi / A sweep counts. */
 int svl_td_run(svl_ctx *ctx, int Nt, double dt, int solveA, double eps, const svl_buf *eps_field,

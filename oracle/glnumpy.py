@@ -280,6 +280,126 @@ def td_run(g, dt, Nt, eps, mt, kappa, sigma, H, psi, a, b, stop_psi=1e-6, stop_A
 
 
 # ----------------------------------------------------------------------------------------------
+# fixed vortices (svirl/vars/fixed_vortices.py:176-246; svirl/solvers/td.py:120-155, 207-216, 252-325)
+# ----------------------------------------------------------------------------------------------
+
+def snap_vortices(g, vx, vy, vv, correction="cell centers"):
+    """Integer vorticity, positions on cell centres / vertices (fixed_vortices.py:114-127)."""
+    r_t = g.dtype
+    vx, vy, vv = [np.asarray(v, dtype=r_t) for v in (vx, vy, vv)]
+    vv = np.round(vv)
+    if correction == "cell centers":
+        vx = g.dx * (np.round(vx / g.dx + 0.5) - 0.5)
+        vy = g.dy * (np.round(vy / g.dy + 0.5) - 0.5)
+    elif correction == "vertices":
+        vx, vy = g.dx * np.round(vx / g.dx), g.dy * np.round(vy / g.dy)
+    return vx, vy, vv
+
+
+def irregular_potential(g, vx, vy, vv):
+    """(a_i, b_i) = sum_k v_k * lattice gradient of atan2(y - y_k, x - x_k) (fixed_vortices.py:192-206)."""
+    r_t = g.dtype
+    xg = np.repeat((g.dx * np.arange(g.Nx, dtype=r_t))[:, None], g.Ny, axis=1)       # mesh/grid.py:35-60
+    yg = np.repeat((g.dy * np.arange(g.Ny, dtype=r_t))[None, :], g.Nx, axis=0)
+    ai = np.zeros((g.Nx - 1, g.Ny), dtype=r_t)
+    bi = np.zeros((g.Nx, g.Ny - 1), dtype=r_t)
+    for x0, y0, v in zip(vx, vy, vv):
+        th = np.arctan2(yg - y0, xg - x0)
+        th -= th[0, 0]
+        ai += v * g.idx * np.diff(th, axis=0)
+        bi += v * g.idy * np.diff(th, axis=1)
+    return ai, bi
+
+
+def phase_lock_list(g, vx, vy, radius):
+    """The reference's lock list: i-indices of the nodes within `radius` of a fixed vortex
+    (np.where(mask)[0], fixed_vortices.py:236), later used as FLAT node numbers."""
+    r_t = g.dtype
+    xg = np.repeat((g.dx * np.arange(g.Nx, dtype=r_t))[:, None], g.Ny, axis=1)
+    yg = np.repeat((g.dy * np.arange(g.Ny, dtype=r_t))[None, :], g.Nx, axis=0)
+    m = np.zeros((g.Nx, g.Ny), dtype=bool)
+    for x0, y0 in zip(vx, vy):
+        m |= np.square(xg - x0) + np.square(yg - y0) <= np.square(radius)
+    return np.where(m)[0].astype(np.int32)
+
+
+def _fold_flat(g, xa, xb, ya, yb, sign, n_flat):
+    """x[0:n_flat] += sign*y[0:n_flat] on the PACKED edge array (a then b, x fastest): xpy_r / xmy_r are
+    launched with N = Nx*Ny on Na+Nb entries (td.py:128,151,260,322), so all of a and the first
+    Nx*Ny - Na = Ny entries of b change (quirk Q5)."""
+    Na = (g.Nx - 1) * g.Ny
+    fa, fb = xa.T.reshape(-1).copy(), xb.T.reshape(-1).copy()
+    ga, gb = ya.T.reshape(-1), yb.T.reshape(-1)
+    na = min(n_flat, Na)
+    fa[:na] += sign * ga[:na]
+    nb = max(0, min(n_flat - Na, fb.size))
+    fb[:nb] += sign * gb[:nb]
+    return fa.reshape(g.Ny, g.Nx - 1).T.astype(g.dtype), fb.reshape(g.Ny - 1, g.Nx).T.astype(g.dtype)
+
+
+def _phase_lock(g, psi, lock_ns):
+    """psi[n] <- |psi[n]| on the flat node list (svirl/cuda/td.h:296-307)."""
+    if lock_ns is None or not lock_ns.size:
+        return psi
+    flat = psi.T.reshape(-1).copy()
+    flat[lock_ns] = np.abs(flat[lock_ns])
+    return flat.reshape(g.Ny, g.Nx).T.astype(g.ctype)
+
+
+def td_psi_run_fixed(g, dt, Nt, eps, mt, psi, a, b, ai, bi, lock_ns=None, stop_psi=1e-6, rand_t=1, counts=None):
+    """td(eqn='order_parameter') with fixed vortices (svirl/solvers/td.py:221-231): the irregular
+    potential is folded in ONCE before the loop and folded out after EVERY step (reference quirk).
+    Returns psi, a, b, rand_t."""
+    r_t = g.dtype
+    stop_psi = max(stop_psi, 1e-6 if r_t is np.float32 else 1e-12)
+    N = g.Nx * g.Ny
+    a, b = _fold_flat(g, a, b, ai, bi, +1, N)
+    for _ in range(Nt):
+        psi, ns = td_psi_solve(g, dt, eps, mt, a, b, psi, stop_psi, 0.0, rand_t)
+        rand_t = (rand_t + 1) & 0xffffffff
+        psi = _phase_lock(g, psi, lock_ns)
+        a, b = _fold_flat(g, a, b, ai, bi, -1, N)
+        if counts is not None:
+            counts.append((ns, 0))
+    return psi, a, b, rand_t
+
+
+def td_run_fixed(g, dt, Nt, eps, mt, kappa, sigma, H, psi, a, b, ai, bi, lock_ns=None, stop_psi=1e-6,
+                 stop_A=1e-6, rand_t=1, counts=None):
+    """TD outer loop with fixed vortices (td.py:342-367 with :120-155, :207-216, :252-325).  Per step:
+    A += A_i (first N entries); psi-solve; phase lock; A -= A_i; A_i += A; A-solve with the link phase
+    taken from A_i (a separate buffer: no Q1 aliasing); A_i -= A_new.  Returns psi, a, b, ai, bi, rand_t."""
+    solveA = not np.isposinf(kappa)
+    r_t = g.dtype
+    stop_psi = max(stop_psi, 1e-6 if r_t is np.float32 else 1e-12)
+    stop_A = max(stop_A, 1e-6 if r_t is np.float32 else 1e-12)
+    N = g.Nx * g.Ny
+    for _ in range(Nt):
+        a, b = _fold_flat(g, a, b, ai, bi, +1, N)
+        psi, ns = td_psi_solve(g, dt, eps, mt, a, b, psi, stop_psi, 0.0, rand_t)
+        rand_t = (rand_t + 1) & 0xffffffff
+        psi = _phase_lock(g, psi, lock_ns)
+        a, b = _fold_flat(g, a, b, ai, bi, -1, N)
+        na = 0
+        if solveA:
+            ai, bi = _fold_flat(g, ai, bi, a, b, +1, N)
+            kappa2, rho = r_t(r_t(kappa) ** 2), r_t(1.0 / sigma)
+            a_rhs, b_rhs = a.copy(), b.copy()
+            ca, cb = a, b
+            for s in range(1024):
+                ca_, cb_, r, a_rhs, b_rhs = a_sweep(g, dt, kappa2, rho, H, mt, psi, ai, bi, a_rhs, b_rhs, ca, cb, 0.0, s, rand_t)
+                ca, cb = ca_, cb_
+                if stop_test(r, stop_A, r_t):
+                    break
+            a, b, na = ca, cb, s + 1
+            rand_t = (rand_t + 1) & 0xffffffff
+            ai, bi = _fold_flat(g, ai, bi, a, b, -1, N)
+        if counts is not None:
+            counts.append((ns, na))
+    return psi, a, b, ai, bi, rand_t
+
+
+# ----------------------------------------------------------------------------------------------
 # E3: free energy (svirl/cuda/observables.h:251-362 + observables.py:124-149)
 # ----------------------------------------------------------------------------------------------
 

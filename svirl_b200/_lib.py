@@ -41,6 +41,9 @@ SIGNATURES = {
     "svl_td_a_sweep": ([_p, _d, _d, _d, _d, _p, _p, _p, _p, _p, _d, _u32, _u32, _pd], _i),
     "svl_td_psi_solve": ([_p, _d, _d, _p, _p, _p, _d, _u32, _d, C.POINTER(_i)], _i),
     "svl_td_a_solve": ([_p, _d, _d, _d, _d, _p, _p, _d, _u32, _d, C.POINTER(_i)], _i),
+    "svl_td_a_solve_ph": ([_p, _d, _d, _d, _d, _p, _p, _p, _d, _u32, _d, C.POINTER(_i)], _i),
+    "svl_edge_axpy_flat": ([_p, _p, _p, _d, C.c_longlong], _i),
+    "svl_phase_lock": ([_p, _p, _p, _i], _i),
     "svl_td_run": ([_p, _i, _d, _i, _d, _p, _d, _d, _d, _p, _p, _d, _d, C.POINTER(_u32), _d, _d,
                     C.POINTER(C.c_longlong)], _i),
     "svl_free_energy": ([_p, _d, _d, _p, _d, _p, _p, _p, _pd], _i),

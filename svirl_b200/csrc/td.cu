@@ -401,6 +401,7 @@ extern "C" int svl_td_psi_solve(svl_ctx *c, double dt, double eps, const svl_buf
 // sweep's own input, which is what lets a_tile.cu fuse sweeps (2m, 2m+1) into one launch.
 struct ASolveArgs {
     double dt, kappa2, rho, H; const svl_buf *psi; double lang_c; uint32_t rand_t;
+    const svl_buf *ph_fixed;      // fixed vortices: the link phase comes from this buffer in every sweep (no Q1 aliasing)
 };
 
 // Rotation state of the A solve.  `cur` holds iterate s, `even` the newest even iterate <= s
@@ -425,7 +426,14 @@ static int a_advance(svl_ctx *c, const ASolveArgs &A, AIter &it, int upto) {
         int K = 1;
         svl_buf *out;
         bool pushed = false;                         // the tile kernel waits for its halos and pushes its own
-        if ((it.s & 1) == 0) {
+        if (A.ph_fixed) {
+            // separate, unperturbed phase buffer (svirl/solvers/td.py:257-266): plain ping-pong of per-node sweeps
+            out = it.cur == it.S1 ? it.S2 : it.S1;
+            SVL_TRY(svl_slab_wait(c));
+            SVL_TRY(svl_launch_a_sweep(c, A.dt, A.kappa2, A.rho, A.H, A.psi, A.ph_fixed, it.B0, it.cur, out, A.lang_c,
+                                       A.rand_t, noise, c->d_resid + it.s));
+            it.cur = it.even = out;
+        } else if ((it.s & 1) == 0) {
             out = it.cur == it.S1 ? it.S2 : it.S1;
             if (c->opt_a_kernel >= 1) {
                 K = upto - it.s >= 2 ? 2 : 1;
@@ -452,8 +460,23 @@ static int a_advance(svl_ctx *c, const ASolveArgs &A, AIter &it, int upto) {
     return 0;
 }
 
+static int a_solve(svl_ctx *c, double dt, double kappa2, double rho, double H, const svl_buf *psi, const svl_buf *ph_fixed,
+                   svl_buf *ab, double lang_c, uint32_t rand_t, double stop_eps, int *sweeps_out);
+
 extern "C" int svl_td_a_solve(svl_ctx *c, double dt, double kappa2, double rho, double H, const svl_buf *psi,
                               svl_buf *ab, double lang_c, uint32_t rand_t, double stop_eps, int *sweeps_out) {
+    return a_solve(c, dt, kappa2, rho, H, psi, nullptr, ab, lang_c, rand_t, stop_eps, sweeps_out);
+}
+
+extern "C" int svl_td_a_solve_ph(svl_ctx *c, double dt, double kappa2, double rho, double H, const svl_buf *psi,
+                                 const svl_buf *ab_phase, svl_buf *ab, double lang_c, uint32_t rand_t, double stop_eps,
+                                 int *sweeps_out) {
+    SVL_REQUIRE(ab_phase && ab_phase->kind == SVL_EDGE && ab_phase != ab, "ab_phase must be a distinct SVL_EDGE buffer");
+    return a_solve(c, dt, kappa2, rho, H, psi, ab_phase, ab, lang_c, rand_t, stop_eps, sweeps_out);
+}
+
+static int a_solve(svl_ctx *c, double dt, double kappa2, double rho, double H, const svl_buf *psi, const svl_buf *ph_fixed,
+                   svl_buf *ab, double lang_c, uint32_t rand_t, double stop_eps, int *sweeps_out) {
     SVL_REQUIRE(c, "null context");
     SVL_REQUIRE(psi && psi->kind == SVL_NODE_C, "psi must be SVL_NODE_C");
     SVL_REQUIRE(ab && ab->kind == SVL_EDGE, "ab must be SVL_EDGE");
@@ -462,7 +485,7 @@ extern "C" int svl_td_a_solve(svl_ctx *c, double dt, double kappa2, double rho, 
     SVL_TRY(svl_scratch_edge(c, 0, &it.S1));
     SVL_TRY(svl_scratch_edge(c, 1, &it.S2));
     it.reset();
-    ASolveArgs A = {dt, kappa2, rho, H, psi, lang_c, rand_t};
+    ASolveArgs A = {dt, kappa2, rho, H, psi, lang_c, rand_t, ph_fixed};
     SVL_CHECK(cudaMemsetAsync(c->d_resid, 0, SVL_MAX_SWEEPS * sizeof(unsigned long long), c->stream));
     int done = 0, nstop = -1;
     while (nstop < 0) {
@@ -519,5 +542,62 @@ extern "C" int svl_td_run(svl_ctx *c, int Nt, double dt, int solveA, double eps,
             if (sweeps) sweeps[1] += n;
         }
     }
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- fixed-vortex helpers
+// x[n] += sign * y[n] for the first n_flat entries of the reference's PACKED edge array (a then b):
+// the reference launches xpy_r / xmy_r with N = Nx*Ny on an array of Na + Nb entries
+// (svirl/solvers/td.py:128,151,260,322 -- SURVEY quirk Q5), so all of a and only the first
+// N - Na = Ny entries of b are touched.  Reproduced on the pitched planes.
+template <typename R>
+__global__ void k_edge_axpy_flat(Geo g, R *xa, R *xb, const R *ya, const R *yb, R sign, long long n_flat) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = g.j0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.Nx || j >= g.j1) return;
+    const size_t n = g.at(i, j);
+    const long long Na = (long long)(g.Nx - 1) * g.Ny;
+    if (i < g.Nx - 1 && (long long)i + (long long)(g.Nx - 1) * j < n_flat) xa[n] += sign * ya[n];
+    if (j < g.Ny - 1 && Na + (long long)i + (long long)g.Nx * j < n_flat) xb[n] += sign * yb[n];
+}
+
+extern "C" int svl_edge_axpy_flat(svl_ctx *c, svl_buf *x, const svl_buf *y, double sign, long long n_flat) {
+    SVL_REQUIRE(c && x && y && x->kind == SVL_EDGE && y->kind == SVL_EDGE, "two SVL_EDGE buffers required");
+    dim3 b(32, 8), gr((c->g.Nx + 31) / 32, (c->g.j1 - c->g.j0 + 7) / 8);
+    if (c->rsize == 4)
+        k_edge_axpy_flat<float><<<gr, b, 0, c->stream>>>(c->g, (float *)x->p[0], (float *)x->p[1], (const float *)y->p[0],
+                                                         (const float *)y->p[1], (float)sign, n_flat);
+    else
+        k_edge_axpy_flat<double><<<gr, b, 0, c->stream>>>(c->g, (double *)x->p[0], (double *)x->p[1], (const double *)y->p[0],
+                                                          (const double *)y->p[1], sign, n_flat);
+    SVL_CHECK(cudaGetLastError());
+    c->stat_launches += 1;
+    return 0;
+}
+
+// order_parameter_phase_lock (svirl/cuda/td.h:296-307): psi[n] <- |psi[n]| for the listed flat node
+// indices (duplicates allowed: the operation is idempotent)
+template <typename C>
+__global__ void k_phase_lock(Geo g, C *psi, const int *ns, int count) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= count) return;
+    const int n = ns[l], i = n % g.Nx, j = n / g.Nx;
+    if (j < g.j0 || j >= g.j1) return;
+    C *p = psi + g.at(i, j);
+    C v = *p;
+    v.x = sqrt(v.x * v.x + v.y * v.y);      // abs(complex): hypot without the scaling, like pycuda::abs for moderate values
+    v.y = 0;
+    *p = v;
+}
+
+extern "C" int svl_phase_lock(svl_ctx *c, svl_buf *psi, const svl_buf *lock_ns, int count) {
+    SVL_REQUIRE(c && psi && psi->kind == SVL_NODE_C, "psi must be SVL_NODE_C");
+    SVL_REQUIRE(lock_ns && lock_ns->kind == SVL_FLAT && lock_ns->esize == 4 && (size_t)count <= lock_ns->n,
+                "lock_ns must be a flat int32 buffer of at least count entries");
+    if (count <= 0) return 0;
+    if (c->rsize == 4) k_phase_lock<float2><<<svl_nblocks(count, 128), 128, 0, c->stream>>>(c->g, (float2 *)psi->p[0], (const int *)lock_ns->p[0], count);
+    else k_phase_lock<double2><<<svl_nblocks(count, 128), 128, 0, c->stream>>>(c->g, (double2 *)psi->p[0], (const int *)lock_ns->p[0], count);
+    SVL_CHECK(cudaGetLastError());
+    c->stat_launches += 1;
     return 0;
 }

@@ -75,7 +75,10 @@ class VortexDetector(object):
             self.vars._psi.sync()
             self.vars._vp.sync()
             a, b = self.vars._vp.get_vec_h()
-            a_ai, b_bi = a, b                    # no irregular potential in this build (row f1)
+            a_ai, b_bi = a, b
+            if self.fixed_vortices._vpi is not None:      # triangulation uses regular + irregular (vortex_detector.py:43-47)
+                ai, bi = self.fixed_vortices.irregular_vector_potential
+                a_ai, b_bi = a + ai, b + bi
             psi = self.vars.order_parameter
             theta = np.angle(psi)
             dx, dy, pi = cfg.dx, cfg.dy, np.pi

@@ -80,7 +80,69 @@ class TD(object):
         p = self.params
         return float(np.asarray(p.linear_coefficient_scalar_h()).reshape(-1)[0]), _h(p.linear_coefficient_h())
 
-    def _run(self, Nt, dt, do_psi=True, do_A=True):
+    def _run_fixed_vortices(self, Nt, dt, do_psi, do_A, pre_once):
+        """Time stepping with fixed vortices and / or phase lock: the irregular potential is folded
+        into the regular one around each solve, step by step, exactly in the reference's order and with
+        its element counts (svirl/solvers/td.py:120-155, 207-216, 252-325; SURVEY quirk Q5: the fold
+        covers the first Nx*Ny entries of the packed edge array only, and after the A-solve the
+        irregular potential absorbs the CHANGE of the regular one on those entries)."""
+        p, fv = self.params, self.fixed_vortices
+        ctx = self.par.ctx
+        self.vars._psi.push()
+        self.vars._vp.push()
+        eps, epsf = self._eps_args()
+        psi, ab = self.vars.order_parameter_h(), self.vars.vector_potential_h()
+        vpi = fv._vpi.get_d_obj() if fv._vpi is not None else None
+        if fv._vpi is not None:
+            fv._vpi.push()
+        lock = fv._phase_lock_ns
+        n = C.c_int()
+        N = int(cfg.N)
+        k2, rho, H = float(p.gl_parameter_squared_h()), float(p._rho), float(p.homogeneous_external_field)
+
+        def fold(x, y, sign):
+            _lib.call("svl_edge_axpy_flat", ctx, x.handle, y.handle, float(sign), N)
+
+        if do_psi and pre_once and vpi is not None:
+            fold(ab, vpi, +1.0)                      # eqn='order_parameter': added once, removed every step (td.py:227-231)
+        for _ in range(int(Nt)):
+            if do_psi:
+                if not pre_once and vpi is not None:
+                    fold(ab, vpi, +1.0)
+                _lib.call("svl_td_psi_solve", ctx, float(dt), eps, epsf, ab.handle, psi.handle,
+                          float(p.order_parameter_Langevin_coefficient), int(self._random_t),
+                          float(cfg.stop_criterion_order_parameter), C.byref(n))
+                self._random_t = np.uint32(int(self._random_t) + 1)
+                self.sweeps_order_parameter += n.value
+                if lock is not None:
+                    _lib.call("svl_phase_lock", ctx, psi.handle, lock.get_d_obj().handle, int(lock.size))
+                if vpi is not None:
+                    fold(ab, vpi, -1.0)
+            if do_A and self.solveA:
+                if vpi is not None:
+                    fold(vpi, ab, +1.0)
+                    _lib.call("svl_td_a_solve_ph", ctx, float(self.dt), k2, rho, H, psi.handle, vpi.handle, ab.handle,
+                              float(p.vector_potential_Langevin_coefficient), int(self._random_t),
+                              float(cfg.stop_criterion_vector_potential), C.byref(n))
+                else:
+                    _lib.call("svl_td_a_solve", ctx, float(self.dt), k2, rho, H, psi.handle, ab.handle,
+                              float(p.vector_potential_Langevin_coefficient), int(self._random_t),
+                              float(cfg.stop_criterion_vector_potential), C.byref(n))
+                self._random_t = np.uint32(int(self._random_t) + 1)
+                self.sweeps_vector_potential += n.value
+                if vpi is not None:
+                    fold(vpi, ab, -1.0)
+        self.vars._psi.need_dtoh_sync()
+        if do_A and self.solveA:
+            self.vars._vp.need_dtoh_sync()           # the psi-only path leaves the host copy of A as it was (td.py:216)
+        # the reference never marks the irregular potential as changed on the device, so its host copy (what
+        # irregular_vector_potential and the vortex detector read) keeps the values set by the user while the
+        # device copy drifts; same here
+
+    def _run(self, Nt, dt, do_psi=True, do_A=True, pre_once=False):
+        fv = self.fixed_vortices
+        if fv._vpi is not None or fv._phase_lock_ns is not None:
+            return self._run_fixed_vortices(Nt, dt, do_psi, do_A, pre_once)
         p = self.params
         self.vars._psi.push()
         self.vars._vp.push()
@@ -115,7 +177,7 @@ class TD(object):
         if eqn == "order_parameter":
             self._set_iterator_options('order_parameter', dt=dt, Nt=Nt, T=T)
             self._warn_order_parameter()
-            self._run(self.Nt, self.dt, do_psi=True, do_A=False)
+            self._run(self.Nt, self.dt, do_psi=True, do_A=False, pre_once=True)
         elif eqn == "vector_potential":
             if not self.solveA:
                 return

@@ -398,3 +398,54 @@ def test_cg_line_search_rescue_on_large_grid_coefficients():
     # well-scaled coefficients: the reference call is kept as is
     cg._CG__c[:] = c
     assert np.allclose(cg._cg_alpha_min_guarded(), cg._cg_alpha_min(), rtol=0, atol=0) and cg.line_search_rescues == 1
+
+
+@pytest.mark.parametrize("name", ["td_f64_k2_fixed", "td_f32_kinf_fixed", "td_f64_k3_fixed_nolock"])
+def test_td_fixed_vortices(name):
+    """fixed vortices + phase lock through GLSolver against the unmodified reference
+    (oracle/make_golden_fixed.py), quirks included: partial fold of the packed edge array, lock list of
+    i-indices, drifting device copy of the irregular potential, stale host copies."""
+    from svirl_b200 import GLSolver
+    d = load_golden(name)
+    m = d["meta"]
+    f64 = m["dtype"] == "float64"
+    kw = {k: v for k, v in m.items() if k not in ("Nt", "Nt2", "dtype")}
+    kw["dtype"] = np.dtype(m["dtype"]).type
+    kw["fixed_vortices"] = [[8.2, 15.1], [7.3, 11.0], [1, -1]]
+    if "mt" in d:
+        kw["material_tiling"] = d["mt"]
+    gl = GLSolver(**kw)
+    fv = gl.params.fixed_vortices
+    assert np.array_equal(gl.vars.order_parameter, d["psi0"])
+    vx, vy, vv = fv.fixed_vortices
+    assert np.array_equal(vx, d["fvx"]) and np.array_equal(vy, d["fvy"]) and np.array_equal(vv, d["fvv"])
+    ai, bi = fv.irregular_vector_potential
+    t0 = 1e-13 if f64 else 1e-5
+    assert np.abs(ai - d["ai0"]).max() < t0 and np.abs(bi - d["bi0"]).max() < t0
+    lock = fv._phase_lock_ns.get_h().ravel() if fv._phase_lock_ns is not None else np.zeros(0, np.int32)
+    assert np.array_equal(lock, d["lock_ns"])
+    gl.solve.td(dt=0.1, Nt=m["Nt"])
+    td = gl.solve._td
+    tol = 1e-10 if f64 else 1e-4
+    if f64:
+        assert (td.sweeps_order_parameter, td.sweeps_vector_potential) == (int(d["sweeps_psi"]), int(d["sweeps_A"]))
+    a, b = gl.vars.vector_potential
+    assert relerr(gl.vars.order_parameter, d["psi1"]) < tol
+    assert relerr(a, d["a1"]) < tol and relerr(b, d["b1"]) < tol
+    assert np.abs(fv._vpi.get_d_obj().get() - d["vpi_dev1"]).max() < tol * max(np.abs(d["vpi_dev1"]).max(), 1.0)
+    ai, bi = fv.irregular_vector_potential                       # host copy: unchanged, like the reference's
+    assert np.abs(ai - d["ai0"]).max() < t0 and np.abs(bi - d["bi0"]).max() < t0
+    assert abs(gl.observables.free_energy - d["obs_E"]) < (1e-9 if f64 else 2e-4) * max(abs(d["obs_E"]), 1.0)
+    assert np.abs(fv.fixed_vortices_phase - d["phase"]).max() < (1e-11 if f64 else 1e-3)
+    vx, vy, vv = gl.vortex_detector.vortices
+    assert np.array_equal(vv, d["obs_vv"])
+    if f64:
+        assert np.allclose(vx, d["obs_vx"], rtol=0, atol=1e-8) and np.allclose(vy, d["obs_vy"], rtol=0, atol=1e-8)
+    gl.solve.td(dt=0.1, Nt=m["Nt2"], eqn="order_parameter")
+    assert int(td._random_t) == int(d["rand_t"])
+    if f64:
+        assert td.sweeps_order_parameter == int(d["sweeps_psi2"])
+    assert relerr(gl.vars.order_parameter, d["psi2"]) < tol
+    a, b = gl.vars.vector_potential                              # host copy stays at the stage-one values
+    assert relerr(a, d["a2"]) < tol and relerr(b, d["b2"]) < tol
+    assert np.abs(gl.vars._vp.get_d_obj().get() - d["vp_dev2"]).max() < tol * max(np.abs(d["vp_dev2"]).max(), 1.0)

@@ -151,3 +151,58 @@ def test_hash_rng_known_values():
         return s ^ (s >> 15)
     n = np.arange(0, 5000, 7, dtype=np.uint32)
     assert np.array_equal(O.rand_hash(n), np.array([wang(int(x)) for x in n], dtype=np.uint32))
+
+
+FIXED_CASES = ["td_f64_k2_fixed", "td_f32_kinf_fixed", "td_f64_k3_fixed_nolock"]
+
+
+@pytest.mark.parametrize("name", FIXED_CASES)
+def test_td_fixed_vortices(name):
+    """irregular potential, phase-lock list, td() and td(eqn='order_parameter') with fixed
+    vortices against the unmodified reference (oracle/make_golden_fixed.py), including its quirks: partial
+    fold of the packed edge array, lock list of i-indices, drift of the device copy of A_i."""
+    d = load_golden(name)
+    m = d["meta"]
+    dtype = np.dtype(m["dtype"]).type
+    f64 = dtype is np.float64
+    g = O.Grid(m["Nx"], m["Ny"], m["dx"], m["dy"], dtype)
+    mt = d["mt"] if "mt" in d else None
+    kappa = m.get("gl_parameter", np.inf)
+    vx, vy, vv = O.snap_vortices(g, [8.2, 15.1], [7.3, 11.0], [1, -1], m["fixed_vortices_correction"])
+    assert np.array_equal(vx, d["fvx"]) and np.array_equal(vy, d["fvy"]) and np.array_equal(vv, d["fvv"])
+    ai, bi = O.irregular_potential(g, vx, vy, vv)
+    assert np.abs(ai - d["ai0"]).max() < (1e-13 if f64 else 1e-5) and np.abs(bi - d["bi0"]).max() < (1e-13 if f64 else 1e-5)
+    lock = O.phase_lock_list(g, vx, vy, m["phase_lock_radius"]) if "phase_lock_radius" in m else np.zeros(0, np.int32)
+    assert np.array_equal(lock, d["lock_ns"])
+    counts = []
+    psi, a, b, ai1, bi1, rt = O.td_run_fixed(g, 0.1, m["Nt"], 1.0, mt, kappa, m.get("normal_conductivity", 1.0),
+                                             m["homogeneous_external_field"], d["psi0"], d["a0"], d["b0"], d["ai0"],
+                                             d["bi0"], lock, rand_t=m["random_seed"], counts=counts)
+    tol = 1e-12 if f64 else 1e-4
+    if f64:
+        assert (sum(c[0] for c in counts), sum(c[1] for c in counts)) == (int(d["sweeps_psi"]), int(d["sweeps_A"]))
+    assert np.abs(psi - d["psi1"]).max() < tol
+    assert np.abs(a - d["a1"]).max() < tol and np.abs(b - d["b1"]).max() < tol
+    # the reference's host copy of A_i never changes; its device copy drifts with the A-solves
+    assert np.array_equal(d["ai1_host"], d["ai0"]) and np.array_equal(d["bi1_host"], d["bi0"])
+    packed = np.concatenate([ai1.T.reshape(-1), bi1.T.reshape(-1)])
+    assert np.abs(packed - d["vpi_dev1"]).max() < tol
+    # second stage: td(eqn='order_parameter') continues from the reference's end state
+    Na = (g.Nx - 1) * g.Ny
+    ai_d = d["vpi_dev1"][:Na].reshape(g.Ny, g.Nx - 1).T.astype(dtype)
+    bi_d = d["vpi_dev1"][Na:].reshape(g.Ny - 1, g.Nx).T.astype(dtype)
+    c2 = []
+    psi2, a2, b2, rt2 = O.td_psi_run_fixed(g, 0.1, m["Nt2"], 1.0, mt, d["psi1"], d["a1"], d["b1"], ai_d, bi_d, lock,
+                                           rand_t=rt, counts=c2)
+    assert rt2 == int(d["rand_t"])
+    if f64:
+        assert sum(c[0] for c in c2) == int(d["sweeps_psi2"]) - int(d["sweeps_psi"])
+    assert np.abs(psi2 - d["psi2"]).max() < tol
+    # this path marks only psi as changed: the reference's HOST copy of A stays at the stage-one values while
+    # the device copy has lost A_i (Nt2 - 1) times
+    assert np.array_equal(d["a2"], d["a1"]) and np.array_equal(d["b2"], d["b1"])
+    packed = np.concatenate([a2.T.reshape(-1), b2.T.reshape(-1)])
+    assert np.abs(packed - d["vp_dev2"]).max() < tol
+    # detector on the reference's end state of stage one: triangulation uses a + a_i (host copy)
+    vx_, vy_, vv_ = O.vortices(g, m["homogeneous_external_field"], d["psi1"], d["a1"], d["b1"], d["ai0"], d["bi0"])
+    assert np.array_equal(vv_, d["obs_vv"]) and np.allclose(vx_, d["obs_vx"], rtol=0, atol=1e-9 if f64 else 1e-4)
