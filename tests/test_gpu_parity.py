@@ -449,3 +449,39 @@ def test_td_fixed_vortices(name):
     a, b = gl.vars.vector_potential                              # host copy stays at the stage-one values
     assert relerr(a, d["a2"]) < tol and relerr(b, d["b2"]) < tol
     assert np.abs(gl.vars._vp.get_d_obj().get() - d["vp_dev2"]).max() < tol * max(np.abs(d["vp_dev2"]).max(), 1.0)
+
+
+@pytest.mark.parametrize("shape", [(4, 4), (5, 9), (33, 31), (64, 65), (130, 7)], ids=lambda s: "%dx%d" % s)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_small_and_ragged_grids_against_oracle(shape, dtype):
+    """Edge cases of the geometry: the minimum grid (4x4), sizes below / across one tile and one warp,
+    odd pitches: TDGL (finite kappa, random holes, eps field) and a CG iteration against the NumPy oracle."""
+    import glnumpy as O
+    from svirl_b200 import GLSolver
+    Nx, Ny = shape
+    rs = np.random.RandomState(Nx * 131 + Ny)
+    mt = rs.rand(Nx - 1, Ny - 1) > 0.2
+    eps = (0.7 + 0.3 * rs.rand(Nx, Ny)).astype(dtype)
+    gl = GLSolver(Nx=Nx, Ny=Ny, dx=0.5, dy=0.4, dtype=dtype, gl_parameter=2.0, normal_conductivity=10.0,
+                  homogeneous_external_field=0.1, random_seed=3, material_tiling=mt, linear_coefficient=eps)
+    g = O.Grid(Nx, Ny, 0.5, 0.4, dtype)
+    psi0 = gl.vars.order_parameter
+    a0, b0 = [x.copy() for x in gl.vars.vector_potential]
+    gl.solve.td(dt=0.1, Nt=6)
+    counts = []
+    po, ao, bo, _ = O.td_run(g, 0.1, 6, eps, mt, 2.0, 10.0, 0.1, psi0, a0, b0, rand_t=3, counts=counts)
+    f64 = dtype is np.float64
+    tol = 1e-11 if f64 else 2e-4
+    a1, b1 = gl.vars.vector_potential
+    if f64:
+        td = gl.solve._td
+        assert (td.sweeps_order_parameter, td.sweeps_vector_potential) == (sum(c[0] for c in counts), sum(c[1] for c in counts))
+    assert np.abs(gl.vars.order_parameter - po).max() < tol
+    assert np.abs(a1 - ao).max() < tol and np.abs(b1 - bo).max() < tol
+    k2 = dtype(dtype(2.0) ** 2)
+    z = np.zeros_like
+    Eo = O.free_energy(g, k2, eps, 0.1, mt, po, z(ao), z(bo), ao, bo)
+    assert abs(gl.observables.free_energy - Eo) < (1e-10 if f64 else 2e-4) * max(abs(Eo), 1.0)
+    gl.solve.cg(n_iter=1)
+    _, _, _, Eo1, _ = O.cg_run(g, 1, 2.0, eps, 0.1, mt, po, z(ao), z(bo), ao, bo)
+    assert abs(gl.solve._cg.cg_energies[0] - Eo1[0]) < (1e-8 if f64 else 1e-3) * max(abs(Eo1[0]), 1.0)
