@@ -55,6 +55,18 @@ def workload(name):
     if name == "cfg4inf":
         return dict(name="cfg4inf: CG minimiser 8192^2 fp32 kappa=inf tiled", Nx=8192, Ny=8192, dtype=np.float32,
                     kappa=np.inf, sigma=1.0, H=0.1, tiling=True, eps_field=False, cg=True)
+    if name == "cfg5":        # BASELINE configs[4], strong scaling: the grid is fixed, rows are split over the GPUs
+        return dict(name="cfg5: TDGL kappa=inf 32768^2 fp64, strong scaling, slab-local fields + vortex count", Nx=32768,
+                    Ny=32768, dtype=np.float64, kappa=np.inf, sigma=1.0, H=0.1, tiling=False, eps_field=False, scale="strong")
+    if name == "cfg5k2":
+        return dict(name="cfg5k2: TDGL kappa=2 32768^2 fp64, strong scaling", Nx=32768, Ny=32768, dtype=np.float64,
+                    kappa=2.0, sigma=10.0, H=0.1, tiling=False, eps_field=False, scale="strong")
+    if name == "cfg5w":       # weak scaling: 65536 x 8192 nodes per GPU
+        return dict(name="cfg5w: TDGL kappa=inf 65536 x 8192 per GPU fp64, weak scaling", Nx=65536, Ny=8192,
+                    dtype=np.float64, kappa=np.inf, sigma=1.0, H=0.1, tiling=False, eps_field=False, scale="weak")
+    if name == "cfg5mini":    # the same driver at a size that runs anywhere
+        return dict(name="cfg5mini: TDGL kappa=inf 4096^2 fp64 through the scale driver", Nx=4096, Ny=4096,
+                    dtype=np.float64, kappa=np.inf, sigma=1.0, H=0.1, tiling=False, eps_field=False, scale="strong")
     if name == "cfg1":
         return dict(name="cfg1: README 129^2 fp64 kappa=5", Nx=129, Ny=129, dtype=np.float64, kappa=5.0, sigma=200.0,
                     H=0.1, tiling=False, eps_field=False)
@@ -321,6 +333,89 @@ def bench_cg(args, wl, gl, par, N):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------ scale mode (cfg5)
+def bench_scale(args, wl, rank, world, local):
+    """BASELINE configs[4]: grids whose fields do not fit full-size host arrays, through
+    svirl_b200.scale.ScaleTD (slab-local seeded fields, row slabs over NVLink, GPU vortex count)."""
+    import torch
+    import torch.distributed as dist
+    from svirl_b200 import _lib
+    from svirl_b200.scale import ScaleTD
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    Nx, Ny = wl["Nx"], wl["Ny"] * (world if wl["scale"] == "weak" else 1)
+    N = Nx * Ny
+    t_build = time.perf_counter()
+    st = ScaleTD(Nx, Ny, 0.5, 0.5, wl["dtype"], wl["kappa"], wl["sigma"], wl["H"], 1.0, 1234, 1.0, device_id=local,
+                 distributed=world > 1)
+    t_build = time.perf_counter() - t_build
+    for kv in args.opt:
+        k, v = kv.split("=")
+        _lib.call("svl_set_option", st._ctx, k.encode(), int(v))
+
+    def barrier():
+        st.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    st.td(0.1, max(args.warmup, 3))
+    barrier()
+    s0 = (st.sweeps[0], st.sweeps[1])
+    l0 = st.stat("launches")
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0 = time.perf_counter()
+    _lib.call("svl_event_record", st._ctx, 0)
+    st.td(0.1, args.steps)
+    _lib.call("svl_event_record", st._ctx, 1)
+    ms = C.c_double()
+    _lib.call("svl_event_elapsed_ms", st._ctx, 0, 1, C.byref(ms))
+    npos, nneg = st.vortex_count()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    t = torch.tensor([ms.value, wall, float(npos), float(nneg)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t_ms, wall = float(tm[0]), float(tm[1])
+    else:
+        t_ms = ms.value
+    npos, nneg = int(t[2].item()), int(t[3].item())
+    if rank == 0:
+        sw_psi, sw_A = st.sweeps[0] - s0[0], st.sweeps[1] - s0[1]
+        bpsi, bA = bytes_per_node_sweep(wl)
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = (sw_psi * bpsi + sw_A * bA) * (N // world) / (t_ms * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": N * args.steps / (t_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "higher_is_better": True,
+                "scaling": wl["scale"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl["name"], "Nx": Nx, "Ny": Ny, "dt": 0.1, "seed": 1234,
+                           "l2": "working set exceeds the 126 MB L2", "rows_per_gpu": Ny // world},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "kernel": "psi Jacobi sweep", "bytes_per_node_sweep": bpsi,
+                             "sweeps_psi": int(sw_psi), "sweeps_A": int(sw_A)},
+                "cpu_baseline": None, "clocks": clocks, "gpu_launches": int(st.stat("launches") - l0),
+                "vortices": {"positive": npos, "negative": nneg, "how": "GPU winding pass, reference thresholds"},
+                "build_s": t_build,
+                "e2e": {"value": N * args.steps / wall, "unit": UNIT, "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": int(16 * (npos + nneg) / max(args.steps, 1)),
+                        "api": "ScaleTD.td(dt, Nt) + ScaleTD.vortex_count(): fields stay on the GPUs, the vortex list comes back"}}
+        print(json.dumps(line))
+    st.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -344,7 +439,7 @@ def main():
     wl = workload(args.workload)
     if args.ny_mult > 1:
         wl = dict(wl, Ny=wl["Ny"] * args.ny_mult, name=wl["name"] + " (Ny x%d)" % args.ny_mult)
-    if world > 1 and args.impl == "ours":
+    if world > 1 and args.impl == "ours" and not wl.get("scale"):
         wl = dict(wl, Ny=wl["Ny"] * world, name=wl["name"] + " x%d row slabs (Ny=%d)" % (world, wl["Ny"] * world))
     N = wl["Nx"] * wl["Ny"]
     cfgd = {"workload": wl["name"], "Nx": wl["Nx"], "Ny": wl["Ny"], "dt": 0.1, "seed": 1234,
@@ -367,6 +462,9 @@ def main():
                 "gpu_launches": 0}
         print(json.dumps(line))
         return
+
+    if wl.get("scale"):
+        return bench_scale(args, wl, rank, world, local)
 
     import torch
     import torch.distributed as dist

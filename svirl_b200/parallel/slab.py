@@ -43,16 +43,20 @@ def max_reduce_u64(values, group=None):
 class SlabComm(object):
     """Connects this rank's context to its neighbours and installs the residual reduction."""
 
-    def __init__(self, gl, group=None):
+    def __init__(self, gl, group=None, raw=None):
+        """gl: a GLSolver built with slab=...; or raw = (par_like_with_ctx, psi_handle, ab_handle, (j0, j1)) for
+        drivers that own their buffers (svirl_b200/scale.py)."""
         import torch.distributed as dist
         self.gl, self.group = gl, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        par = gl.par
+        if raw is None:
+            raw = (gl.par, gl.vars.order_parameter_h().handle, gl.vars.vector_potential_h().handle, gl.cfg.slab)
+        par, psi_handle, ab_handle, slab = raw
+        self._par, self._slab = par, tuple(int(x) for x in slab)
         mine = (C.c_char * HANDLE_BYTES)()
-        _lib.call("svl_slab_export", par.ctx, gl.vars.order_parameter_h().handle,
-                  gl.vars.vector_potential_h().handle, C.cast(mine, C.c_void_p))
+        _lib.call("svl_slab_export", par.ctx, psi_handle, ab_handle, C.cast(mine, C.c_void_p))
         gathered = [None] * self.world
-        dist.all_gather_object(gathered, (bytes(mine), tuple(int(x) for x in gl.cfg.slab)), group=group)
+        dist.all_gather_object(gathered, (bytes(mine), self._slab), group=group)
         lo = gathered[self.rank - 1] if self.rank > 0 else None
         hi = gathered[self.rank + 1] if self.rank + 1 < self.world else None
         self._keep = [C.create_string_buffer(x[0], HANDLE_BYTES) if x else None for x in (lo, hi)]
@@ -98,9 +102,9 @@ class SlabComm(object):
     def exchange(self, garray):
         """Refresh the halo rows of psi / A from the neighbours (after host-side edits)."""
         garray.push()
-        _lib.call("svl_slab_exchange", self.gl.par.ctx, garray.get_d_obj().handle)
+        _lib.call("svl_slab_exchange", self._par.ctx, garray.get_d_obj().handle)
 
     def owned_rows(self, arr2d):
         """Rows of a host array indexed [i, j] that this rank owns (node rows)."""
-        j0, j1 = self.gl.cfg.slab
+        j0, j1 = self._slab
         return arr2d[:, j0:min(j1, arr2d.shape[1])]

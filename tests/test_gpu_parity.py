@@ -485,3 +485,32 @@ def test_small_and_ragged_grids_against_oracle(shape, dtype):
     gl.solve.cg(n_iter=1)
     _, _, _, Eo1, _ = O.cg_run(g, 1, 2.0, eps, 0.1, mt, po, z(ao), z(bo), ao, bo)
     assert abs(gl.solve._cg.cg_energies[0] - Eo1[0]) < (1e-8 if f64 else 1e-3) * max(abs(Eo1[0]), 1.0)
+
+
+@pytest.mark.parametrize("case", ["f64_k2", "f32_kinf"])
+def test_scale_driver_equals_glsolver_bitwise(case):
+    """svirl_b200.scale.ScaleTD (slab-sized host buffers, fields generated row band by row band) follows
+    the same trajectory as GLSolver BITWISE, and its GPU vortex count equals the detector's."""
+    from svirl_b200 import GLSolver
+    from svirl_b200.scale import ScaleTD
+    dtype = np.float64 if case.startswith("f64") else np.float32
+    kw = dict(Nx=300, Ny=270, dx=0.5, dy=0.5, dtype=dtype, homogeneous_external_field=0.1, random_seed=1234,
+              gl_parameter=2.0 if "k2" in case else np.inf, normal_conductivity=10.0)
+    gl = GLSolver(**kw)
+    gl.solve.td(dt=0.1, Nt=25)
+    psi, (a, b) = gl.vars.order_parameter, gl.vars.vector_potential
+    sweeps = (gl.solve._td.sweeps_order_parameter, gl.solve._td.sweeps_vector_potential)
+    vx, vy, vv = gl.vortex_detector.vortices
+    gl.par.close()
+    st = ScaleTD(band_rows=64, **kw)
+    st.td(0.1, 25)
+    assert (st.sweeps[0], st.sweeps[1]) == sweeps
+    assert np.array_equal(st.psi_rows(0, 270), psi)
+    assert np.array_equal(st.a_rows(0, 270), a) and np.array_equal(st.b_rows(0, 269), b)
+    assert np.array_equal(st.psi_rows(100, 131), psi[:, 100:131])
+    import glnumpy as O
+    v = O.winding(O.Grid(300, 270, 0.5, 0.5, dtype), 0.1, psi, a, b)        # the detector's winding test on the host
+    ok = (np.abs(v) > 0.5) & (np.abs(v - np.round(v)) < 0.1)
+    assert st.vortex_count() == (int(np.sum(ok & (v > 0))), int(np.sum(ok & (v < 0))))
+    assert vv.size <= int(ok.sum())                                            # triangulation may only reject
+    st.close()
