@@ -187,12 +187,13 @@ template <> __device__ __forceinline__ void sincos_r<float>(float x, float *s, f
     if (fabsf(x) > 20000.0f) { sc_f r = sincosf_slow(x); *s = r.s; *c = r.c; return; }   // out of line, by value
     sincos_fast32(x, s, c);
 }
-// fp64: libdevice's sincos() rounds the quadrant with F2I/I2F conversions, which run on the XU
-// pipe at a small fraction of the FP64 rate -- ncu showed that pipe saturated (150 % "realtime")
-// in every kernel that evaluates link variables.  This version stays on the FP64 pipe: quadrant
-// by the 1.5*2^52 magic-number rounding, 3-term Cody-Waite reduction of pi/2 with FMAs (good for
-// |x| < 1e5), fdlibm's degree-13/-12 minimax kernels on [-pi/4, pi/4] (public-domain coefficients).
-// Max error ~1 ulp (checked against libdevice in tests/test_gpu_parity.py::test_sincos_accuracy).
+// fp64: the library's own sincos.  Quadrant by the 1.5*2^52 magic-number rounding (no F2I/I2F
+// conversions), 3-term Cody-Waite reduction of pi/2 with FMAs (good for |x| < 1e5), fdlibm's degree-13/-12
+// minimax kernels on [-pi/4, pi/4] (public-domain coefficients, kept in constant memory so they are FMA
+// operands instead of per-use immediates), signs flipped through the high word.  Max error <= 2 ulp
+// (tests/test_gpu_parity.py::test_sincos_accuracy); libdevice beyond the range.  ncu on the kernels that
+// evaluate link variables showed them issue-slot bound with libdevice's sincos at ~130 dynamic instructions
+// per link; the branch-free core lets callers interleave many evaluations (a_tile.cu).
 struct sc_d { double s, c; };
 static __device__ __noinline__ sc_d sincos_slow(double x) { sc_d r; sincos(x, &r.s, &r.c); return r; }
 __constant__ double SVL_SC[16] = {
