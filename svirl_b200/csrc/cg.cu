@@ -231,6 +231,8 @@ k_coef(Geo g, R kappa2, R eps, R H, const uint8_t *__restrict__ nf, const typena
        double *partials) {
     typedef typename V2<R>::type C;
     const R dx = (R)g.dx, dy = (R)g.dy, idx = (R)g.idx, idy = (R)g.idy, idx2 = (R)g.idx2, idy2 = (R)g.idy2;
+    // w is 0, 1/2 or 1, so (-w*i2)/3 == -w*(i2/3) bit for bit: the divisions of cg.h:600-640 leave the node loop
+    const R idx2_3 = idx2 / (R)3.0, idy2_3 = idy2 / (R)3.0, idx2_12 = idx2 / (R)12.0, idy2_12 = idy2 / (R)12.0;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int j = g.j0 + blockIdx.y * blockDim.y + threadIdx.y;
     double v[NV];
@@ -258,6 +260,7 @@ k_coef(Geo g, R kappa2, R eps, R H, const uint8_t *__restrict__ nf, const typena
                 if (!on) continue;
                 size_t n1 = dir == 0 ? n + 1 : n + g.P;
                 R w = dir == 0 ? wE : wN, i2 = dir == 0 ? idx2 : idy2, d = dir == 0 ? dx : dy;
+                const R i2_3 = dir == 0 ? idx2_3 : idy2_3, i2_12 = dir == 0 ? idx2_12 : idy2_12;   // Taylor 1/3, 1/12 folded in
                 R ph = 0;
                 if (dir == 0) { if (ae) ph += d * ae[n]; if (a) ph += d * a[n]; }
                 else { if (be) ph += d * be[n]; if (b) ph += d * b[n]; }
@@ -282,20 +285,20 @@ k_coef(Geo g, R kappa2, R eps, R H, const uint8_t *__restrict__ nf, const typena
                     ZMUL(p0, p1, zr, zi);
                     v[1] += (double)(w * i2 * (R)2.0 * zi * dph);
                     v[2] += (double)(w * i2 * zr * dph2);
-                    v[3] += (double)(-w * i2 / (R)3.0 * zi * dph2 * dph);
-                    v[4] += (double)(-w * i2 / (R)12.0 * zr * dph2 * dph2);
+                    v[3] += (double)(-w * i2_3 * zi * dph2 * dph);
+                    v[4] += (double)(-w * i2_12 * zr * dph2 * dph2);
                     ZMUL(p0, d1, zr, zi);
                     ZMUL(d0, p1, z2r, z2i);
                     zr += z2r; zi += z2i;
                     v[6] += (double)(w * i2 * (R)2.0 * zi * dph);
                     v[7] += (double)(w * i2 * zr * dph2);
-                    v[8] += (double)(-w * i2 / (R)3.0 * zi * dph2 * dph);
-                    v[9] += (double)(-w * i2 / (R)12.0 * zr * dph2 * dph2);
+                    v[8] += (double)(-w * i2_3 * zi * dph2 * dph);
+                    v[9] += (double)(-w * i2_12 * zr * dph2 * dph2);
                     ZMUL(d0, d1, zr, zi);
                     v[11] += (double)(w * i2 * (R)2.0 * zi * dph);
                     v[12] += (double)(w * i2 * zr * dph2);
-                    v[13] += (double)(-w * i2 / (R)3.0 * zi * dph2 * dph);
-                    v[14] += (double)(-w * i2 / (R)12.0 * zr * dph2 * dph2);
+                    v[13] += (double)(-w * i2_3 * zi * dph2 * dph);
+                    v[14] += (double)(-w * i2_12 * zr * dph2 * dph2);
 #undef ZMUL
                 }
             }

@@ -214,6 +214,8 @@ k_cgf_coef(CgfState<R> S, const double *__restrict__ beta, const typename V2<R>:
     const Geo &g = S.g;
     const R *const ae_ = EXT ? S.ae : nullptr, *const be_ = EXT ? S.be : nullptr;   // compile-time absent without an external potential
     const R dx = (R)g.dx, dy = (R)g.dy, idx = (R)g.idx, idy = (R)g.idy, idx2 = (R)g.idx2, idy2 = (R)g.idy2;
+    // w is 0, 1/2 or 1, so (-w*i2)/3 == -w*(i2/3) bit for bit: the divisions of cg.h:600-640 leave the node loop
+    const R idx2_3 = idx2 / (R)3.0, idy2_3 = idy2 / (R)3.0, idx2_12 = idx2 / (R)12.0, idy2_12 = idy2 / (R)12.0;
     const R beta_psi = (R)beta[0], beta_A = (R)beta[1];
     const int C1 = NV == 17 ? 5 : 1, C2 = NV == 17 ? 10 : 2, C3 = NV == 17 ? 15 : 3, C4 = NV == 17 ? 16 : 4;
     double v[NV];
@@ -277,6 +279,8 @@ k_cgf_coef(CgfState<R> S, const double *__restrict__ beta, const typename V2<R>:
                         const bool on = dir == 0 ? (f & (NF_PM | NF_PP)) : (f & (NF_MP | NF_PP));
                         if (!on) continue;
                         const R w = dir == 0 ? wE : wN, i2 = dir == 0 ? idx2 : idy2, d = dir == 0 ? dx : dy;
+                        // (1/3, 1/12 of the Taylor terms folded into per-direction constants: no division per node)
+                        const R i2_3 = dir == 0 ? idx2_3 : idy2_3, i2_12 = dir == 0 ? idx2_12 : idy2_12;
                         R ph = 0;
                         if (ae_) ph += d * (dir == 0 ? cur.ea : cur.eb);
                         if (S.a) ph += d * (dir == 0 ? cur.a : cur.b);
@@ -301,20 +305,20 @@ k_cgf_coef(CgfState<R> S, const double *__restrict__ beta, const typename V2<R>:
                             ZMUL(p0, p1, zr, zi);
                             v[1] += (double)(w * i2 * (R)2.0 * zi * dph);
                             v[2] += (double)(w * i2 * zr * dph2);
-                            v[3] += (double)(-w * i2 / (R)3.0 * zi * dph2 * dph);
-                            v[4] += (double)(-w * i2 / (R)12.0 * zr * dph2 * dph2);
+                            v[3] += (double)(-w * i2_3 * zi * dph2 * dph);
+                            v[4] += (double)(-w * i2_12 * zr * dph2 * dph2);
                             ZMUL(p0, d1, zr, zi);
                             ZMUL(d0, p1, z2r, z2i);
                             zr += z2r; zi += z2i;
                             v[6] += (double)(w * i2 * (R)2.0 * zi * dph);
                             v[7] += (double)(w * i2 * zr * dph2);
-                            v[8] += (double)(-w * i2 / (R)3.0 * zi * dph2 * dph);
-                            v[9] += (double)(-w * i2 / (R)12.0 * zr * dph2 * dph2);
+                            v[8] += (double)(-w * i2_3 * zi * dph2 * dph);
+                            v[9] += (double)(-w * i2_12 * zr * dph2 * dph2);
                             ZMUL(d0, d1, zr, zi);
                             v[11] += (double)(w * i2 * (R)2.0 * zi * dph);
                             v[12] += (double)(w * i2 * zr * dph2);
-                            v[13] += (double)(-w * i2 / (R)3.0 * zi * dph2 * dph);
-                            v[14] += (double)(-w * i2 / (R)12.0 * zr * dph2 * dph2);
+                            v[13] += (double)(-w * i2_3 * zi * dph2 * dph);
+                            v[14] += (double)(-w * i2_12 * zr * dph2 * dph2);
 #undef ZMUL
                         }
                     }
