@@ -422,6 +422,8 @@ __global__ void __launch_bounds__(256) k_axy3(Axy3<R> d, R alpha0, R alpha1, con
 
 static int check_state(const svl_buf *psi, const svl_buf *abei, const svl_buf *ab, const svl_buf *epsf) {
     SVL_REQUIRE(psi && psi->kind == SVL_NODE_C, "psi must be SVL_NODE_C");
+    // the sums of the energy / CG kernels are per context: on row slabs they would silently be partial
+    SVL_REQUIRE(!(psi->ctx && psi->ctx->slab_on), "free energy / CG on row slabs is not built yet (TDGL only)");
     SVL_REQUIRE(!ab || ab->kind == SVL_EDGE, "ab must be SVL_EDGE");
     SVL_REQUIRE(!abei || abei->kind == SVL_EDGE, "abei must be SVL_EDGE");
     SVL_REQUIRE(!epsf || epsf->kind == SVL_NODE_R, "eps_field must be SVL_NODE_R");
