@@ -114,6 +114,8 @@ extern "C" int svl_destroy(svl_ctx *c) {
         if (c->psi_s[k]) svl_free(c, c->psi_s[k]);
         if (c->ab_s[k]) svl_free(c, c->ab_s[k]);
     }
+    if (c->cg_s_node) svl_free(c, c->cg_s_node);
+    if (c->cg_s_edge) svl_free(c, c->cg_s_edge);
     cudaFree(c->arena);
     cudaFree(c->board);
     cudaFree(c->nf); cudaFree(c->d_result); cudaFreeHost(c->h_result);
@@ -160,6 +162,7 @@ extern "C" int svl_set_option(svl_ctx *c, const char *name, int v) {
     else if (!strcmp(name, "cg_fused")) c->opt_cg_fused = v;
     else if (!strcmp(name, "resid_board")) c->opt_resid_board = v;
     else if (!strcmp(name, "slab_split")) c->opt_slab_split = v;
+    else if (!strcmp(name, "cg_slabs")) c->opt_cg_slabs = v;           // experimental: CG / energy on row slabs (untested on hardware)
     else if (!strcmp(name, "slab_nocomm")) c->opt_slab_nocomm = v;     // timing experiments only: ranks run uncoupled
     else if (!strcmp(name, "trace")) {                                 // diagnostics: record v launches from now on
         SVL_CHECK(cudaStreamSynchronize(c->stream));

@@ -423,7 +423,8 @@ __global__ void __launch_bounds__(256) k_axy3(Axy3<R> d, R alpha0, R alpha1, con
 static int check_state(const svl_buf *psi, const svl_buf *abei, const svl_buf *ab, const svl_buf *epsf) {
     SVL_REQUIRE(psi && psi->kind == SVL_NODE_C, "psi must be SVL_NODE_C");
     // the sums of the energy / CG kernels are per context: on row slabs they would silently be partial
-    SVL_REQUIRE(!(psi->ctx && psi->ctx->slab_on), "free energy / CG on row slabs is not built yet (TDGL only)");
+    SVL_REQUIRE(!(psi->ctx && psi->ctx->slab_on && !psi->ctx->opt_cg_slabs),
+                "free energy / CG on row slabs is experimental: enable option cg_slabs (TDGL is the validated slab path)");
     SVL_REQUIRE(!ab || ab->kind == SVL_EDGE, "ab must be SVL_EDGE");
     SVL_REQUIRE(!abei || abei->kind == SVL_EDGE, "abei must be SVL_EDGE");
     SVL_REQUIRE(!epsf || epsf->kind == SVL_NODE_R, "eps_field must be SVL_NODE_R");
@@ -442,6 +443,14 @@ static int energy_t(svl_ctx *c, double kappa2, double eps, const svl_buf *epsf, 
                                              EDGE_B(ab, R), c->partials);
     SVL_CHECK(cudaGetLastError());
     c->stat_launches += 1;
+    if (c->slab_on) {      // experimental (option cg_slabs): the per-rank sums are added over the residual board
+        SVL_TRY(svl_finish_sum(c, nb, 1, (double)((R)c->g.dx * (R)c->g.dy), nullptr));
+        SVL_TRY(svl_board_allsum(c, c->d_result, 1));
+        SVL_CHECK(cudaMemcpyAsync(c->h_result, c->d_result, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        SVL_CHECK(cudaStreamSynchronize(c->stream));
+        *E = c->h_result[0];
+        return 0;
+    }
     return svl_finish_sum(c, nb, 1, (double)((R)c->g.dx * (R)c->g.dy), E);
 }
 
@@ -685,6 +694,7 @@ extern "C" int svl_cg_begin(svl_ctx *c, int solveA, int have_prev, double kappa2
                 d_psi->kind == SVL_NODE_C, "psi-side CG buffers must be SVL_NODE_C");
     SVL_REQUIRE(!solveA || (g_A && g_A_prev && d_A && ab && g_A->kind == SVL_EDGE && g_A_prev->kind == SVL_EDGE &&
                             d_A->kind == SVL_EDGE), "A-side CG buffers must be SVL_EDGE");
+    SVL_REQUIRE(c->opt_cg_fused || !c->slab_on, "CG on slabs needs the fused iteration (option cg_fused = 1)");
     if (c->opt_cg_fused)
         return svl_cgf_begin(c, solveA, have_prev, kappa2, eps, epsf, H, psi, abei, ab, g_psi, g_psi_prev, d_psi, g_A,
                              g_A_prev, d_A, beta, c_out);

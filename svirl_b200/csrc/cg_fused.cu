@@ -28,6 +28,7 @@
 template <typename R> struct CgfState {     // what all three kernels read
     Geo g;
     int V;                                  // rows per strip (run time: 32 on large grids, fewer on small ones)
+    int ext_lo, ext_hi;                     // slabs: rows computed beyond [j0, j1) towards a neighbour (sums stay on owned rows)
     R kappa2, eps, H;
     const R *epsf;
     const uint8_t *nf;
@@ -82,11 +83,12 @@ __device__ __forceinline__ void cgf_pf(const void *base, size_t elem, int nelem,
 #define CGF_TILE_LOOP_BEGIN(WOUT, LPAD)                                                            \
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;           \
     const int ntx = (g.Nx + (WOUT) * nwarp - 1) / ((WOUT) * nwarp);                                \
-    const int nty = (g.j1 - g.j0 + S.V - 1) / S.V;                                                 \
+    const int ylo_ = g.j0 - S.ext_lo, yhi_ = g.j1 + S.ext_hi;                                      \
+    const int nty = (yhi_ - ylo_ + S.V - 1) / S.V;                                                 \
     for (int t = blockIdx.x; t < ntx * nty; t += gridDim.x) {                                      \
         const int i = ((t % ntx) * nwarp + warp) * (WOUT) + lane - (LPAD);                         \
-        const int ys = g.j0 + (t / ntx) * S.V;                                                     \
-        const int ye = ys + S.V < g.j1 ? ys + S.V : g.j1;                                          \
+        const int ys = ylo_ + (t / ntx) * S.V;                                                     \
+        const int ye = ys + S.V < yhi_ ? ys + S.V : yhi_;                                          \
         if (i - lane + (LPAD) >= g.Nx) continue;                                                   \
         const bool in = lane >= (LPAD) && lane < (LPAD) + (WOUT) && i < g.Nx;
 #define CGF_TILE_LOOP_END }
@@ -185,7 +187,7 @@ k_cgf_update(CgfState<R> S, const typename V2<R>::type *__restrict__ dpsi, const
                     if (S.a) dB += idx * (bE - cur.b) - idy * (nxt.a - cur.a);
                     e += S.kappa2 * dB * dB;
                 }
-                acc[0] += (double)e;
+                if (y >= g.j0 && y < g.j1) acc[0] += (double)e;          // halo rows (slabs) are updated, not summed
                 psi_out[n] = cur.p;
                 if (SOLVEA) { a_out[n] = cur.a; b_out[n] = cur.b; }
             }
@@ -262,7 +264,8 @@ k_cgf_coef(CgfState<R> S, const double *__restrict__ beta, const typename V2<R>:
             const R dbE = __shfl_down_sync(FULL, cur.db, 1);
             if (in) {
                 const size_t n = g.at(i, y);
-                const unsigned f = cur.f;
+                const unsigned f = (y >= g.j0 && y < g.j1) ? cur.f : 0u;     // halo rows (slabs): direction only, no sums
+                const bool own = y >= g.j0 && y < g.j1;
                 if (f) {
                     R wW, wE, wS, wN, gw;
                     du_w<R>(f, wW, wE, wS, wN, gw);
@@ -323,7 +326,7 @@ k_cgf_coef(CgfState<R> S, const double *__restrict__ beta, const typename V2<R>:
                         }
                     }
                 }
-                if (S.kappa2 > (R)0 && i < g.Nx - 1 && y < g.Ny - 1) {
+                if (own && S.kappa2 > (R)0 && i < g.Nx - 1 && y < g.Ny - 1) {
                     if (NV == 17) {
                         R BH = -S.H;
                         if (ae_) BH += idx * (ebE - cur.eb) - idy * (nxt.ea - cur.ea);
@@ -484,7 +487,8 @@ k_cgf_grad(CgfState<R> S, typename V2<R>::type *__restrict__ gpsi, R *__restrict
                 const R dxdy = dx * dy;
                 gj.x *= dxdy; gj.y *= dxdy;
                 gpsi[n] = gj;
-                if (PREV) {
+                const bool own = y >= g.j0 && y < g.j1;                     // halo rows (slabs): gradient only, no sums
+                if (PREV && own) {
                     v[0] += (double)(gj.x * (gj.x - q.x) + gj.y * (gj.y - q.y));
                     v[1] += (double)(q.x * q.x + q.y * q.y);
                 }
@@ -498,7 +502,7 @@ k_cgf_grad(CgfState<R> S, typename V2<R>::type *__restrict__ gpsi, R *__restrict
                         }
                         w = (R)2.0 * dx * dy * w;
                         ga[n] = w;
-                        if (PREV) { v[2] += (double)(w * (w - qa)); v[3] += (double)(qa * qa); }
+                        if (PREV && own) { v[2] += (double)(w * (w - qa)); v[3] += (double)(qa * qa); }
                     }
                     if (y < g.Ny - 1) {
                         R w = S.kappa2 * cgf_curl_b<R>(g, i, n, S.H, ae_, be_, S.a, S.b);
@@ -508,7 +512,7 @@ k_cgf_grad(CgfState<R> S, typename V2<R>::type *__restrict__ gpsi, R *__restrict
                         }
                         w = (R)2.0 * dx * dy * w;
                         gb[n] = w;
-                        if (PREV) { v[2] += (double)(w * (w - qb)); v[3] += (double)(qb * qb); }
+                        if (PREV && own) { v[2] += (double)(w * (w - qb)); v[3] += (double)(qb * qb); }
                     }
                 }
             }
@@ -556,6 +560,10 @@ static CgfState<R> cgf_state(svl_ctx *c, double kappa2, double eps, const svl_bu
     CgfState<R> S;
     S.g = c->g;
     S.V = cgf_rows(c);
+    // slabs: gradients, directions and updates are also evaluated on two halo rows per neighbour, so only psi / A
+    // need an exchange per iteration (their halos are 8 rows deep); see cgf_end_t
+    S.ext_lo = (c->slab_on && c->has_lo) ? 2 : 0;
+    S.ext_hi = (c->slab_on && c->has_hi) ? 2 : 0;
     S.kappa2 = (R)kappa2; S.eps = (R)eps; S.H = (R)H;
     S.epsf = epsf ? (const R *)epsf->p[0] : nullptr;
     S.nf = c->nf;
@@ -593,6 +601,7 @@ static int cgf_begin_t(svl_ctx *c, int solveA, int have_prev, double kappa2, dou
     double *dbeta = c->d_result + 32;                 // device-resident beta[2]
     if (have_prev) {
         SVL_TRY(svl_finish_sum(c, nb, 4, 1.0, nullptr));          // d_result[0..3], no host read
+        if (c->slab_on) SVL_TRY(svl_board_allsum(c, c->d_result, 4));
         k_cgf_beta<R><<<1, 32, 0, c->stream>>>(c->d_result, dbeta);
         SVL_CHECK(cudaGetLastError());
         c->stat_launches += 1;
@@ -603,8 +612,14 @@ static int cgf_begin_t(svl_ctx *c, int solveA, int have_prev, double kappa2, dou
     }
     // direction update fused with the coefficients; new directions go to scratch planes, then swap
     svl_buf *dn_psi = nullptr, *dn_A = nullptr;
-    SVL_TRY(svl_scratch_node(c, 0, &dn_psi));
-    if (solveA) SVL_TRY(svl_scratch_edge(c, 0, &dn_A));
+    if (c->slab_on) {      // the TD scratch planes belong to the exchanged arena and must stay psi / A planes
+        if (!c->cg_s_node) SVL_TRY(svl_alloc(c, SVL_NODE_C, 0, 0, &c->cg_s_node));
+        if (solveA && !c->cg_s_edge) SVL_TRY(svl_alloc(c, SVL_EDGE, 0, 0, &c->cg_s_edge));
+        dn_psi = c->cg_s_node; dn_A = c->cg_s_edge;
+    } else {
+        SVL_TRY(svl_scratch_node(c, 0, &dn_psi));
+        if (solveA) SVL_TRY(svl_scratch_edge(c, 0, &dn_A));
+    }
     // Quirk Q11: the coefficient kernels use the scalar eps (0.0 when eps is a field)
     S.eps = (R)(epsf ? 0.0 : eps);
 #define COEF17_ARGS S, dbeta, (const C *)g_psi->p[0], gA0, gA1, (const C *)d_psi->p[0], (const R *)d_A->p[0],  \
@@ -624,7 +639,16 @@ static int cgf_begin_t(svl_ctx *c, int solveA, int have_prev, double kappa2, dou
     SVL_TRY(svl_swap(c, d_psi, dn_psi));
     if (solveA) SVL_TRY(svl_swap(c, d_A, dn_A));
     SVL_CHECK(cudaMemcpyAsync(c->h_result + 32, dbeta, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    SVL_TRY(svl_finish_sum(c, solveA ? nb17 : nb, solveA ? 17 : 5, (double)((R)c->g.dx * (R)c->g.dy), c_out));   // one host sync
+    const int nvc = solveA ? 17 : 5;
+    if (c->slab_on) {      // experimental (option cg_slabs): rank-ordered sum over the residual board, then one host sync
+        SVL_TRY(svl_finish_sum(c, solveA ? nb17 : nb, nvc, (double)((R)c->g.dx * (R)c->g.dy), nullptr));
+        SVL_TRY(svl_board_allsum(c, c->d_result, nvc));
+        SVL_CHECK(cudaMemcpyAsync(c->h_result, c->d_result, nvc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        SVL_CHECK(cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < nvc; k++) c_out[k] = c->h_result[k];
+    } else {
+        SVL_TRY(svl_finish_sum(c, solveA ? nb17 : nb, nvc, (double)((R)c->g.dx * (R)c->g.dy), c_out));   // one host sync
+    }
     beta[0] = c->h_result[32];
     if (solveA) beta[1] = c->h_result[33];
     return 0;
@@ -657,6 +681,16 @@ static int cgf_end_t(svl_ctx *c, int solveA, double kappa2, double eps, const sv
     SVL_TRY(svl_swap(c, psi, pn));
     if (solveA) SVL_TRY(svl_swap(c, ab, An));
     double E = 0.0;
+    if (c->slab_on) {      // experimental (option cg_slabs): refresh the 8-row halos of the new state, add the energies
+        SVL_TRY(svl_slab_push_psi(c, psi));
+        if (solveA) SVL_TRY(svl_slab_push_ab(c, ab));
+        SVL_TRY(svl_slab_wait(c));
+        SVL_TRY(svl_finish_sum(c, nb, 1, (double)((R)c->g.dx * (R)c->g.dy), nullptr));
+        SVL_TRY(svl_board_allsum(c, c->d_result, 1));
+        SVL_CHECK(cudaMemcpyAsync(c->h_result, c->d_result, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        SVL_CHECK(cudaStreamSynchronize(c->stream));
+        E = c->h_result[0];
+    } else
     SVL_TRY(svl_finish_sum(c, nb, 1, (double)((R)c->g.dx * (R)c->g.dy), &E));
     if (E_out) *E_out = E;
     return 0;

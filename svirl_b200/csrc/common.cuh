@@ -84,6 +84,7 @@ struct svl_ctx {
     // scratch for solvers (allocated lazily)
     svl_buf *psi_s[2];
     svl_buf *ab_s[2];
+    svl_buf *cg_s_node, *cg_s_edge;   // slabs: scratch for the CG directions (psi_s / ab_s live in the exchanged arena)
     // reductions
     double *partials;              // device, capacity partial_cap doubles
     size_t partial_cap;
@@ -95,7 +96,7 @@ struct svl_ctx {
     // vortex candidates
     long long *d_cand; double *d_candv; unsigned long long *d_ncand; size_t cand_cap;
     // options / stats
-    int opt_psi_kernel, opt_psi_k, opt_tma, opt_graphs, opt_a_kernel, opt_cg_fused, opt_resid_board, opt_slab_nocomm, opt_slab_split;
+    int opt_psi_kernel, opt_psi_k, opt_tma, opt_graphs, opt_a_kernel, opt_cg_fused, opt_resid_board, opt_slab_nocomm, opt_slab_split, opt_cg_slabs;
     int pred_psi, pred_A;          // sweep counts of the previous solve
     int pred_psi2, pred_A2;        // ... and of the one before (trend)
     double stat_launches, stat_replays, stat_psi_sweeps, stat_A_sweeps;
@@ -143,6 +144,7 @@ int svl_slab_push_psi(svl_ctx *c, const svl_buf *buf);       // boundary rows of
 int svl_slab_push_ab(svl_ctx *c, const svl_buf *buf);
 int svl_slab_wait(svl_ctx *c);                               // wait until all pushes so far have arrived
 int svl_board_allmax(svl_ctx *c, int first, int count);      // d_resid[first..] <- MAX over ranks (peer memory)
+int svl_board_allsum(svl_ctx *c, double *dvals, int count);  // dvals[0..count) <- SUM over ranks, rank order (peer memory)
 // In-kernel push (tile kernels): the tiles that own the first / last `depth` rows store their results
 // into the neighbours' halo rows as well and the last of them publishes the epoch.
 struct SlabPush {

@@ -289,6 +289,50 @@ k_board_allmax(BoardArgs B, unsigned long long *d_resid, int first, int count, u
     }
 }
 
+// Same exchange for sums (CG on slabs): every rank adds the contributions in RANK ORDER, so all ranks get
+// the same bits and the host line search stays in lockstep.
+__global__ void __launch_bounds__(64)
+k_board_allsum(BoardArgs B, double *vals, int count, unsigned long long epoch) {
+    const int par = (int)(epoch & 1ull);
+    const size_t mine = ((size_t)(par * SVL_MAX_RANKS + B.rank)) * SVL_MAX_SWEEPS;
+    for (int r = 0; r < B.world; r++)
+        for (int i = threadIdx.x; i < count; i += blockDim.x)
+            B.peer[r][mine + i] = (unsigned long long)__double_as_longlong(vals[i]);
+    __syncthreads();
+    if ((int)threadIdx.x < B.world) {
+        __threadfence_system();
+        unsigned long long *e = B.peer[threadIdx.x] + BOARD_WORDS + B.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(e), "l"(epoch) : "memory");
+        const unsigned long long *w = B.peer[B.rank] + BOARD_WORDS + threadIdx.x;
+        unsigned long long v = 0;
+        long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
+            if (clock64() - t0 > 20000000000ll) __trap();
+        } while (v < epoch);
+    }
+    __syncthreads();
+    const unsigned long long *own = B.peer[B.rank] + (size_t)par * SVL_MAX_RANKS * SVL_MAX_SWEEPS;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < B.world; r++) s += __longlong_as_double((long long)__ldcv(own + (size_t)r * SVL_MAX_SWEEPS + i));
+        vals[i] = s;
+    }
+}
+
+int svl_board_allsum(svl_ctx *c, double *dvals, int count) {
+    SVL_REQUIRE(c->board_world > 1, "sums over slabs need the residual board (svl_slab_board_connect)");
+    SVL_REQUIRE(count > 0 && count <= SVL_MAX_SWEEPS, "too many values");
+    BoardArgs B;
+    memset(&B, 0, sizeof(B));
+    for (int r = 0; r < c->board_world; r++) B.peer[r] = c->board_peer[r];
+    B.rank = c->board_rank; B.world = c->board_world;
+    c->board_epoch += 1;
+    k_board_allsum<<<1, 64, 0, c->stream>>>(B, dvals, count, c->board_epoch);
+    SVL_CHECK(cudaGetLastError());
+    return 0;
+}
+
 int svl_board_allmax(svl_ctx *c, int first, int count) {
     BoardArgs B;
     memset(&B, 0, sizeof(B));

@@ -16,6 +16,10 @@ def run(kw, Nt, slab):
     from svirl_b200 import GLSolver
     gl = GLSolver(slab=slab, **kw)
     gl.solve.td(dt=0.1, Nt=Nt)
+    if os.environ.get("SLAB_CG"):          # experimental: CG iterations on slabs (option cg_slabs), compared below
+        gl.par.set_option("cg_slabs", 1)
+        gl.solve.cg(n_iter=int(os.environ["SLAB_CG"]))
+        print("rank %s cg energies %s" % (os.environ.get("RANK"), [float(e) for e in gl.solve._cg.cg_energies]), flush=True)
     td = gl.solve._td
     psi = gl.vars._psi.get_d_obj().get()
     ab = gl.vars._vp.get_d_obj().get()
