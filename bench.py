@@ -221,6 +221,10 @@ def cpu_reference_steps(wl, nsteps, warmup=0):
         el = time.perf_counter() - t0
         return N * nsteps / el, dict(kind="port", cores=1, sweeps=sweeps, seconds=el, band=band)
     lib = C.CDLL(so)
+    try:       # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm uses every host core
+        C.CDLL("libgomp.so.1").omp_set_num_threads(int(os.cpu_count() or 1))
+    except OSError:
+        pass
     fn = lib.simt_launch_iterate_order_parameter_jacobi_step
     real = C.c_float if dt_ is np.float32 else C.c_double
     cplx = np.complex64 if dt_ is np.float32 else np.complex128
