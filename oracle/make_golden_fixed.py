@@ -45,12 +45,24 @@ def fixed_case(svirl, name, Nt, Nt2, **kw):
     vx, vy, vv = gl.vortex_detector.vortices
     d["obs_vx"], d["obs_vy"], d["obs_vv"] = vx, vy, vv
     d["phase"] = fv.fixed_vortices_phase
+    # observables and a few CG iterations on a COPY of the state: both see external + irregular (params.py:195-203)
+    ae, be = gl.params.external_irregular_vector_potential
+    d["ae"], d["be"] = ae.copy(), be.copy()
+    d["obs_B"] = gl.observables.magnetic_field
+    jx, jy = gl.observables.supercurrent_density
+    d["obs_jsx"], d["obs_jsy"] = jx, jy
     gl.solve.td(dt=0.1, Nt=Nt2, eqn="order_parameter")
     d["psi2"], d["a2"], d["b2"] = state(gl)          # a2, b2: the host copy, which this path leaves stale (= a1, b1)
     d["vp_dev2"] = np.asarray(gl.vars._vp.get_d_obj().get()).ravel().copy()   # packed device copy (a then b)
     c = refrun.launch_counts()
     d["sweeps_psi2"] = c.get("iterate_order_parameter_jacobi_step", 0)
     d["rand_t"] = int(gl.solve._td._random_t)
+    # stage three: CG from the stage-two state (host copies; the device copy of A differs, see above)
+    d["psi3_in"], d["a3_in"], d["b3_in"] = state(gl)
+    gl.vars.vector_potential = (d["a3_in"], d["b3_in"])          # make device = host, so the fixture is self-contained
+    gl.solve.cg(n_iter=3)
+    d["cg_E"] = np.array(gl.solve._cg.cg_energies, dtype=np.float64)
+    d["psi3"], d["a3"], d["b3"] = state(gl)
     meta = {k: v for k, v in kw.items() if np.isscalar(v) and not callable(v) and k != "dtype"}
     meta["dtype"] = np.dtype(kw.get("dtype", np.float64)).name
     meta["Nt"], meta["Nt2"] = Nt, Nt2

@@ -203,6 +203,16 @@ def test_td_fixed_vortices(name):
     assert np.array_equal(d["a2"], d["a1"]) and np.array_equal(d["b2"], d["b1"])
     packed = np.concatenate([a2.T.reshape(-1), b2.T.reshape(-1)])
     assert np.abs(packed - d["vp_dev2"]).max() < tol
+    # observables of stage one and the CG iterations of stage three see external + irregular potential
+    f_tol = 1e-12 if f64 else 1e-5
+    assert np.abs(d["ae"] - d["ai0"]).max() < f_tol and np.abs(d["be"] - d["bi0"]).max() < f_tol
+    assert np.allclose(O.magnetic_field(g, d["ae"], d["be"], d["a1"], d["b1"]), d["obs_B"], rtol=f_tol, atol=10 * f_tol)
+    jx, jy = O.supercurrent_density(g, mt, d["psi1"], d["ae"], d["be"], d["a1"], d["b1"])
+    assert np.allclose(jx, d["obs_jsx"], rtol=f_tol, atol=10 * f_tol) and np.allclose(jy, d["obs_jsy"], rtol=f_tol, atol=10 * f_tol)
+    _, _, _, E3, _ = O.cg_run(g, 3, kappa, 1.0, m["homogeneous_external_field"], mt, d["psi3_in"], d["ae"], d["be"],
+                              d["a3_in"], d["b3_in"])
+    assert np.allclose(E3[:2], d["cg_E"][:2], rtol=1e-9 if f64 else 1e-3)
+    assert np.allclose(E3, d["cg_E"][:len(E3)], rtol=1e-4 if f64 else 1e-2)
     # detector on the reference's end state of stage one: triangulation uses a + a_i (host copy)
     vx_, vy_, vv_ = O.vortices(g, m["homogeneous_external_field"], d["psi1"], d["a1"], d["b1"], d["ai0"], d["bi0"])
     assert np.array_equal(vv_, d["obs_vv"]) and np.allclose(vx_, d["obs_vx"], rtol=0, atol=1e-9 if f64 else 1e-4)
