@@ -183,6 +183,30 @@ class ScaleTD(object):
         ok = (np.abs(v) > 0.5) & (np.abs(v - np.round(v)) < 0.1)
         return int(np.sum(ok & (v > 0))), int(np.sum(ok & (v < 0)))
 
+    def vortices(self, band_rows=512):
+        """(x, y, vorticity) of the vortices in this slab's cells, ascending cell index: the GPU candidate pass
+        followed by the vectorised host triangulation (observables/triangulate.py, bit-identical to the
+        reference's scalar arithmetic on every fixture), row band by row band.  Not yet exercised on hardware
+        at full scale; the pieces (candidates, row getters, triangulation) are tested separately."""
+        from svirl_b200.observables.triangulate import triangulate
+        cells, _ = self.vortex_candidates()
+        Nxc = self.Nx - 1
+        rows = cells // Nxc
+        dx, dy, H = self.dtype(self.dx), self.dtype(self.dy), self.dtype(self.H)
+        out = []
+        top = min(self.j1, self.Ny - 1)
+        for r0 in range(self.j0, top, band_rows):
+            r1 = min(r0 + band_rows, top)
+            sel = cells[(rows >= r0) & (rows < r1)]
+            if sel.size == 0:
+                continue
+            psi, a, b = self.psi_rows(r0, r1 + 1), self.a_rows(r0, r1 + 1), self.b_rows(r0, r1)
+            out.append(triangulate(sel, psi, a, b, a, b, H, dx, dy, np.int32(Nxc), r0, self.dtype))
+        if not out:
+            z = np.zeros(0, dtype=self.dtype)
+            return z, z.copy(), z.copy()
+        return tuple(np.concatenate([o[k] for o in out]) for k in range(3))
+
     def close(self):
         if getattr(self, "_ctx", None):
             lib = _lib.load()
