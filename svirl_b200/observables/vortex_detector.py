@@ -84,7 +84,16 @@ class VortexDetector(object):
             dx, dy, pi = cfg.dx, cfg.dy, np.pi
             H = self.params.homogeneous_external_field
             found = []
-            for n in self._candidates():
+            cand = self._candidates()
+            if cand.size > 4096:
+                # many vortices: the same arithmetic on whole arrays (bit-identical, tests/test_triangulate_host.py)
+                from .triangulate import triangulate
+                tx, ty, tv = triangulate(cand, psi, a, b, a_ai, b_bi, H, dx, dy, cfg.Nxc, 0, cfg.dtype)
+                self._detected_vortices = np.stack([tx, ty, tv], axis=1).astype(cfg.dtype).reshape(-1, 3)
+                self.solver.vortices_detected = True
+                d = self._detected_vortices
+                return d[:, 0], d[:, 1], d[:, 2]
+            for n in cand:
                 i, j = self.unflatten_c(int(n))   # np.int32 like the reference: dx*i promotes to float64
                 ip, jp = i + 1, j + 1
                 t_00, t_p0, t_pp, t_0p = theta[i, j], theta[ip, j], theta[ip, jp], theta[i, jp]
