@@ -83,6 +83,15 @@ size_t svl_buf_size(const svl_buf *buf);                    /* elements in the f
 int svl_h2d_rows(svl_ctx *ctx, svl_buf *dst, int part, int r0, int r1, const void *src);
 int svl_d2h_rows(svl_ctx *ctx, void *dst, const svl_buf *src, int part, int r0, int r1);
 
+/* Host helper for seeded fields at scale: numpy's legacy Mersenne-Twister stream (np.random.seed / np.random.rand,
+ * svirl/vars/vars.py:103-106).  key[624], *pos = RandomState(seed).get_state()[1:3]; skips `skip` doubles, then writes
+ * n doubles; the state advances. */
+int svl_mt19937_doubles(uint32_t *key, int *pos, unsigned long long skip, double *out, unsigned long long n);
+
+/* psi0[n] = (1 - level*u1[n]) * exp(i*pi*level*(2*u2[n] - 1)) (svirl/vars/vars.py:106) for n values, written as
+ * complex128 (complex_bytes 16) or complex64 (8); host arithmetic, bit-identical to the reference's numpy expression. */
+int svl_seeded_psi(const double *u1, const double *u2, unsigned long long n, double level, void *out, int complex_bytes);
+
 /* material tiling -> per-node flag plane (bits mm,mp,pm,pp: svirl/cuda/td.h:48-57).
  * mt == NULL: no tiling (all in-range cells are material). Must be called once before solving
  * and again whenever the tiling changes (mesh/grid.py:103-120). */

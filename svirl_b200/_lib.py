@@ -68,6 +68,8 @@ SIGNATURES = {
     "svl_set_reduce_callback": ([_p, _p], _i),
     "svl_set_reduce_callback_device": ([_p, _p], _i),
     "svl_get_stream": ([_p], _p),
+    "svl_mt19937_doubles": ([C.POINTER(_u32), C.POINTER(_i), C.c_ulonglong, _pd, C.c_ulonglong], _i),
+    "svl_seeded_psi": ([_pd, _pd, C.c_ulonglong, _d, _p, _i], _i),
     "svl_sum": ([_p, _p, _sz, _pd], _i),
     "svl_sum_v": ([_p, _p, _sz, _i, _pd], _i),
 }

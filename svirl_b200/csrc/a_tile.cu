@@ -34,6 +34,7 @@ struct ATileArgs {
     unsigned long long *slots;
     const unsigned long long *wait_flags;
     unsigned long long wait_epoch;
+    SpinGuard sg;                  // bound of the spin waits on the neighbours' flags
     int has_lo, has_hi;
     SlabPush push;                 // slabs: in-kernel push of the output's boundary rows
     int push_expect[2];
@@ -105,12 +106,7 @@ k_a_tile(const __grid_constant__ ATileArgs A, const __grid_constant__ CUtensorMa
                 if (!(sdir == 0 ? A.has_lo : A.has_hi)) continue;
                 const int rows_own = g.j1 - g.j0, top = (by + 1) * TYO < rows_own ? (by + 1) * TYO : rows_own;
                 if (sdir == 0 ? (by * TYO - K >= 0) : (top + K <= rows_own)) continue;   // box stays inside the slab
-                unsigned long long v = 0;
-                long long t0 = clock64();
-                do {
-                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(A.wait_flags + sdir) : "memory");
-                    if (clock64() - t0 > 20000000000ll) __trap();
-                } while (v < A.wait_epoch);
+                svl_spin_ge(A.wait_flags + sdir, A.wait_epoch, A.sg);
             }
         }
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a_smem_u32(bar)), "r"(S::tx_bytes) : "memory");
@@ -149,12 +145,10 @@ k_a_tile(const __grid_constant__ ATileArgs A, const __grid_constant__ CUtensorMa
     load_rhs();
     // ---- wait for the boxes: one warp polls, the barrier releases the rest
     if (tid < 32) {
-        uint32_t ok = 0;
-        for (uint32_t it = 0; !ok; it++) {
+        uint32_t ok = 0;       // no iteration bound: thread 0 may still be waiting for a neighbour's halo flag
+        while (!ok)
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                          : "=r"(ok) : "r"(a_smem_u32(bar)) : "memory");
-            if (it > (1u << 24)) __trap();
-        }
     }
     __syncthreads();
 
@@ -353,6 +347,7 @@ int svl_launch_a_tile(svl_ctx *c, int K, double dt, double kappa2, double rho, d
     A.slots = resid_slots;
     if (c->slab_on && !c->opt_slab_nocomm) {
         A.wait_flags = c->flags; A.wait_epoch = svl_slab_epoch(c); A.has_lo = c->has_lo; A.has_hi = c->has_hi;
+        A.sg = svl_spin_guard(c);
         svl_slab_mark_waited(c);
         SVL_TRY(svl_slab_push_fused(c, out, &A.push));          // after wait_epoch: this launch's own push
     }

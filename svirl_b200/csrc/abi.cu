@@ -3,6 +3,7 @@
 // svirl/parallel/utils.py (copy_dtod) of the reference.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 
 static thread_local char g_err[1024] = "";
 
@@ -93,6 +94,13 @@ extern "C" int svl_create(svl_ctx **out, int device_id, int Nx, int Ny, double d
     SVL_CHECK(cudaMemsetAsync(c->d_counter, 0, 16 * sizeof(unsigned int), c->stream));
     SVL_CHECK(cudaMalloc(&c->d_ncand, sizeof(unsigned long long)));
     for (int k = 0; k < 8; k++) SVL_CHECK(cudaEventCreate(&c->ev[k]));
+    SVL_CHECK(cudaHostAlloc(&c->h_err, sizeof(int), cudaHostAllocMapped));
+    *c->h_err = 0;
+    SVL_CHECK(cudaHostGetDevicePointer(&c->d_err, c->h_err, 0));
+    {   // bound of the spin waits on peer GPUs: off unless asked for (SVL_SPIN_TIMEOUT_MS or option "spin_timeout_ms")
+        const char *e = getenv("SVL_SPIN_TIMEOUT_MS");
+        c->spin_limit = e ? (long long)(atof(e) * 2.0e6) : 0;
+    }
     c->opt_psi_kernel = 2;
     c->opt_psi_k = 4;
     c->opt_tma = 1;
@@ -122,6 +130,7 @@ extern "C" int svl_destroy(svl_ctx *c) {
     cudaFree(c->d_resid); cudaFreeHost(c->h_resid); cudaFree(c->d_counter);
     cudaFree(c->partials); cudaFree(c->d_cand); cudaFree(c->d_candv); cudaFree(c->d_ncand);
     for (int k = 0; k < 8; k++) cudaEventDestroy(c->ev[k]);
+    cudaFreeHost(c->h_err);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->stream2);
     cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); cudaEventDestroy(c->ev_go);
@@ -129,10 +138,19 @@ extern "C" int svl_destroy(svl_ctx *c) {
     return 0;
 }
 
+int svl_peer_error(svl_ctx *c) {
+    if (c->h_err && *c->h_err) {
+        *c->h_err = 0;
+        svl_set_error("a spin wait on a peer GPU timed out (option spin_timeout_ms): a rank is late or gone");
+        return 4;
+    }
+    return 0;
+}
+
 extern "C" int svl_synchronize(svl_ctx *c) {
     SVL_REQUIRE(c, "null context");
     SVL_CHECK(cudaStreamSynchronize(c->stream));
-    return 0;
+    return svl_peer_error(c);
 }
 
 // CUDA events on the stream every kernel of this context is launched on (torch.cuda.Event would
@@ -158,6 +176,7 @@ extern "C" int svl_set_option(svl_ctx *c, const char *name, int v) {
     else if (!strcmp(name, "psi_k")) { SVL_REQUIRE(v >= 1 && v <= SVL_HALO, "psi_k out of range"); c->opt_psi_k = v; }
     else if (!strcmp(name, "tma")) c->opt_tma = v;
     else if (!strcmp(name, "graphs")) c->opt_graphs = v;
+    else if (!strcmp(name, "spin_timeout_ms")) c->spin_limit = (long long)v * 2000000ll;   // ~2 GHz clock64 ticks; 0 = wait forever
     else if (!strcmp(name, "a_kernel")) c->opt_a_kernel = v;
     else if (!strcmp(name, "cg_fused")) c->opt_cg_fused = v;
     else if (!strcmp(name, "resid_board")) c->opt_resid_board = v;
@@ -369,6 +388,78 @@ int svl_scratch_node(svl_ctx *c, int k, svl_buf **out) {
 int svl_scratch_edge(svl_ctx *c, int k, svl_buf **out) {
     if (!c->ab_s[k]) SVL_TRY(svl_alloc(c, SVL_EDGE, 0, 0, &c->ab_s[k]));
     *out = c->ab_s[k];
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- seeded fields at scale (host)
+// The reference seeds psi with numpy's LEGACY generator (np.random.seed + np.random.rand, svirl/vars/vars.py:93-109):
+// MT19937 with 53-bit doubles (a >> 5, b >> 6).  Walking that stream in the interpreter costs ~15 ns per draw; at
+// 32768^2 (2^31 draws) that dominated the build of a run.  Same recurrence here, on the state exported by
+// numpy.random.RandomState(seed).get_state(), so the stream is bit-identical (tests/test_scale_host.py).
+static inline void mt_twist(uint32_t *mt) {
+    const uint32_t UP = 0x80000000u, LO = 0x7fffffffu, MA = 0x9908b0dfu;
+    int kk = 0;
+    for (; kk < 624 - 397; kk++) { uint32_t y = (mt[kk] & UP) | (mt[kk + 1] & LO); mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? MA : 0u); }
+    for (; kk < 623; kk++) { uint32_t y = (mt[kk] & UP) | (mt[kk + 1] & LO); mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? MA : 0u); }
+    uint32_t y = (mt[623] & UP) | (mt[0] & LO);
+    mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? MA : 0u);
+}
+static inline uint32_t mt_next(uint32_t *mt, int *pos) {
+    if (*pos >= 624) { mt_twist(mt); *pos = 0; }
+    uint32_t y = mt[(*pos)++];
+    y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+    return y;
+}
+extern "C" int svl_mt19937_doubles(uint32_t *key, int *pos, unsigned long long skip, double *out, unsigned long long n) {
+    SVL_REQUIRE(key && pos && (out || n == 0) && *pos >= 0 && *pos <= 624, "bad MT19937 state");
+    // skipping a double = skipping two 32-bit outputs; whole blocks of 624 need the twist only
+    unsigned long long s = 2ull * skip;
+    while (s > 0) {
+        if (*pos >= 624) { mt_twist(key); *pos = 0; }
+        unsigned long long take = (unsigned long long)(624 - *pos);
+        if (take > s) take = s;
+        *pos += (int)take; s -= take;
+    }
+    auto temper = [](uint32_t y) { y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18); return y; };
+    const double inv53 = 1.0 / 9007199254740992.0;           // exact power of two: x * 2^-53 == x / 2^53 bit for bit
+    unsigned long long k = 0;
+    while (k < n) {
+        if (*pos >= 624) { mt_twist(key); *pos = 0; }
+        unsigned long long take = (unsigned long long)((624 - *pos) / 2);
+        if (take > n - k) take = n - k;
+        if (take == 0) {                                      // odd position: one double straddles two blocks
+            const uint32_t a = mt_next(key, pos) >> 5, b = mt_next(key, pos) >> 6;
+            out[k++] = (a * 67108864.0 + b) * inv53;
+            continue;
+        }
+        const uint32_t *m = key + *pos;
+        double *o = out + k;
+        for (unsigned long long q = 0; q < take; q++) {       // branch-free: vectorises
+            const uint32_t a = temper(m[2 * q]) >> 5, b = temper(m[2 * q + 1]) >> 6;
+            o[q] = (a * 67108864.0 + b) * inv53;
+        }
+        *pos += (int)(2 * take); k += take;
+    }
+    return 0;
+}
+
+// psi0[n] = (1 - level*u1[n]) * exp(i*pi*level*(2*u2[n] - 1))   (svirl/vars/vars.py:106), evaluated like numpy does
+// it for arrays -- the phase has a zero real part, so numpy's complex exp reduces to libm's cos / sin of
+// (level*pi)*(2*u2 - 1), and the real-by-complex product to two roundings -- without numpy's six array temporaries.
+// Bit-identical to the numpy expression on this platform (tests/test_scale_host.py); callers split n over threads.
+extern "C" int svl_seeded_psi(const double *u1, const double *u2, unsigned long long n, double level, void *out,
+                              int complex_bytes) {
+    SVL_REQUIRE(u1 && u2 && out && (complex_bytes == 8 || complex_bytes == 16), "bad argument");
+    const double lpi = level * 3.141592653589793;
+    for (unsigned long long k = 0; k < n; k++) {
+        const double m = 1.0 - level * u1[k];
+        const double y = lpi * (2.0 * u2[k] - 1.0);
+        double sn, cs;
+        sincos(y, &sn, &cs);
+        const double re = m * cs, im = m * sn;
+        if (complex_bytes == 16) { ((double *)out)[2 * k] = re; ((double *)out)[2 * k + 1] = im; }
+        else { ((float *)out)[2 * k] = (float)re; ((float *)out)[2 * k + 1] = (float)im; }
+    }
     return 0;
 }
 

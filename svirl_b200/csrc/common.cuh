@@ -125,7 +125,18 @@ struct svl_ctx {
     // diagnostics: per-launch timestamps of the slab tile kernels (option "trace" = number of launches)
     unsigned long long *trace;
     int trace_n, trace_cap;
+    // bounded spin waits on peers (option "spin_timeout_ms", default 0 = wait forever): on a timeout the
+    // waiting kernel raises *d_err (host-mapped pinned word) and carries on; the host turns it into an error
+    long long spin_limit;          // clock64 cycles, 0 = unbounded
+    int *h_err, *d_err;
 };
+
+// what a kernel needs to bound a spin wait on a peer
+struct SpinGuard {
+    long long limit;               // clock64 cycles, 0 = wait forever
+    int *err;                      // host-visible flag raised on a timeout
+};
+static inline SpinGuard svl_spin_guard(const svl_ctx *c) { SpinGuard s = {c->spin_limit, c->d_err}; return s; }
 
 static inline int svl_nblocks(size_t n, int b) { return (int)((n + b - 1) / b); }
 
@@ -159,11 +170,27 @@ int svl_slab_push_fused(svl_ctx *c, const svl_buf *out, SlabPush *info);   // ac
 unsigned long long svl_slab_epoch(svl_ctx *c);               // pushes issued so far (what a consumer must wait for)
 void svl_slab_mark_waited(svl_ctx *c);                       // the next kernel waits by itself
 // abi.cu
+int svl_peer_error(svl_ctx *c);                              // non-zero (and svl_last_error set) if a bounded peer wait timed out
 int svl_scratch_node(svl_ctx *c, int k, svl_buf **out);
 int svl_scratch_edge(svl_ctx *c, int k, svl_buf **out);
 
 // ----------------------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
+// Spin until *p >= epoch (a word written by a peer GPU with st.release.sys).  No wall-clock trap: a rank may
+// legitimately lag by any amount (host I/O, line search); with a limit set, a timeout raises the host-visible
+// error word and returns false -- the context survives and the next host call reports the failure.
+__device__ __forceinline__ bool svl_spin_ge(const unsigned long long *p, unsigned long long epoch, const SpinGuard &sg) {
+    unsigned long long v = 0;
+    const long long t0 = clock64();
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        if (v >= epoch) return true;
+        if (sg.limit > 0 && clock64() - t0 > sg.limit) {
+            if (sg.err) { *(volatile int *)sg.err = 1; __threadfence_system(); }
+            return false;
+        }
+    }
+}
 template <typename R> __device__ __forceinline__ void sincos_r(R x, R *s, R *c);
 // fp32: branch-free Cody-Waite reduction (3-term pi/2) + minimax polynomials on [-pi/4, pi/4]
 // (max abs error 7.6e-8 ~ 1.3 ulp for |x| < 2e4, measured against double; same class as sincosf,

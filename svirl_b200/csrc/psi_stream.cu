@@ -65,11 +65,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    // bounded wait (~2 s): a broken descriptor must fail the launch, not hang the GPU
-    if (mbar_try_wait(bar, parity)) return;
-    long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity))
-        if (clock64() - t0 > 4000000000ll) __trap();
+    while (!mbar_try_wait(bar, parity)) {}
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar) {
     asm volatile(

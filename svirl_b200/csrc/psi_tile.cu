@@ -33,6 +33,7 @@ struct TileArgs {
     int push_expect[2];            // tiles that contribute to the lo / hi push
     int row0, nrow, row1, nrow1;   // tile rows this launch covers: [row0, row0+nrow) then [row1, row1+nrow1)
     int permute;                   // slabs, single launch: process the first / last tile row last
+    SpinGuard sg;                  // bound of the spin waits (halo flags, TMA barrier)
     unsigned long long *trace;     // slabs, diagnostics: [0] first CTA start, [1] last CTA end, [2] longest flag wait,
                                    // [3] time the last flag wait ended (all %globaltimer ns), or null
 };
@@ -112,13 +113,8 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
     auto gtime = [&]() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
     auto wait_side = [&](int sdir) {
         if (flags_seen[sdir] || !(sdir == 0 ? A.has_lo : A.has_hi)) return;
-        unsigned long long v = 0;
-        long long t0 = clock64();
         const unsigned long long g0 = A.trace ? gtime() : 0ull;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(A.wait_flags + sdir) : "memory");
-            if (clock64() - t0 > 20000000000ll) __trap();
-        } while (v < A.wait_epoch);
+        svl_spin_ge(A.wait_flags + sdir, A.wait_epoch, A.sg);
         if (A.trace) { const unsigned long long g1 = gtime(); atomicMax(A.trace + 2, g1 - g0); atomicMax(A.trace + 3, g1); }
         flags_seen[sdir] = true;
     };
@@ -178,12 +174,12 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
         const int nfd = xg0 - (((xg0 + 1024) / 16) * 16 - 1024);
         // ---- wait for this tile's boxes: one warp polls, the barrier releases the rest
         if (tid < 32) {
+            // (thread 0 may be spinning on a neighbour's halo flag before it issues the boxes: no iteration
+            // bound here; a broken descriptor faults the launch by itself)
             uint32_t ok = 0;
-            for (uint32_t it = 0; !ok; it++) {
+            while (!ok)
                 asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                              : "=r"(ok) : "r"(t_smem_u32(bar)), "r"(phase) : "memory");
-                if (it > (1u << 24)) __trap();           // broken descriptor: fail the launch, do not hang
-            }
         }
         phase ^= 1;
         __syncthreads();      // also: everybody is done with the previous tile's exchange buffers
@@ -228,7 +224,9 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
             const R nwy = ((f & (NF_MM | NF_PM)) ? (R)1 : (R)0) + ((f & (NF_MP | NF_PP)) ? (R)1 : (R)0);
             qq.x *= act; qq.y *= act;
             const R D = (R)1.0 + dt * (qq.x * qq.x + qq.y * qq.y - e + (idx2 * nwx + idy2 * nwy));
-            const R d = rcp_r(D);
+            // inactive / out-of-domain nodes stay exactly 0 (td.h:117 writes psi_next = 0): D may vanish there
+            // (dt*eps == 1), and 0 * inf would seed NaNs that the zero-weight links then spread
+            const R d = f ? rcp_r(D) : (R)0;
             psi[v] = p0; q[v] = qq; La[v] = la; Lb[v] = lb; di[v] = d;
             const int xi = (r + 1) * XW + col + 1;
             xb0[xi] = p0;
@@ -486,6 +484,7 @@ int svl_launch_psi_tile(svl_ctx *c, int K, double dt, double eps, const svl_buf 
     A.noise = lang_c > 1.0e-32 ? 1 : 0;
     A.same_rhs = rhs->p[0] == psi->p[0];
     A.out = out->p[0]; A.slots = resid_slots;
+    A.sg = svl_spin_guard(c);
     if (c->slab_on && !c->opt_slab_nocomm) {
         A.wait_flags = c->flags; A.wait_epoch = svl_slab_epoch(c); A.has_lo = c->has_lo; A.has_hi = c->has_hi;
         svl_slab_mark_waited(c);

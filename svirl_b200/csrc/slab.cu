@@ -58,15 +58,10 @@ k_push(PushDesc d, unsigned long long epoch, unsigned int *count) {
     }
 }
 
-__global__ void k_wait_flags(const unsigned long long *flags, int has_lo, int has_hi, unsigned long long epoch) {
+__global__ void k_wait_flags(const unsigned long long *flags, int has_lo, int has_hi, unsigned long long epoch, SpinGuard sg) {
     for (int s = 0; s < 2; s++) {
         if (!(s == 0 ? has_lo : has_hi)) continue;
-        unsigned long long v = 0;
-        long long t0 = clock64();
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + s) : "memory");
-            if (clock64() - t0 > 20000000000ll) __trap();      // ~10 s: a neighbour died
-        } while (v < epoch);
+        svl_spin_ge(flags + s, epoch, sg);
     }
 }
 
@@ -148,7 +143,7 @@ int svl_slab_wait(svl_ctx *c) {
     if (!c->slab_on || c->opt_slab_nocomm) return 0;
     unsigned long long e = c->epoch_psi + c->epoch_A;
     if (e == c->waited) return 0;
-    k_wait_flags<<<1, 1, 0, c->stream>>>(c->flags, c->has_lo, c->has_hi, e);
+    k_wait_flags<<<1, 1, 0, c->stream>>>(c->flags, c->has_lo, c->has_hi, e, svl_spin_guard(c));
     SVL_CHECK(cudaGetLastError());
     c->waited = e;
     return 0;
@@ -239,7 +234,7 @@ extern "C" int svl_slab_exchange(svl_ctx *c, svl_buf *buf) {
     else { svl_set_error("slab exchange: only psi / ab buffers are registered"); return 2; }
     SVL_TRY(svl_slab_wait(c));
     SVL_CHECK(cudaStreamSynchronize(c->stream));
-    return 0;
+    return svl_peer_error(c);
 }
 
 // ----------------------------------------------------------------------------- residual board
@@ -254,6 +249,7 @@ extern "C" int svl_slab_exchange(svl_ctx *c, svl_buf *buf) {
 struct BoardArgs {
     unsigned long long *peer[SVL_MAX_RANKS];
     int rank, world;
+    SpinGuard sg;
 };
 
 __global__ void __launch_bounds__(256)
@@ -270,12 +266,7 @@ k_board_allmax(BoardArgs B, unsigned long long *d_resid, int first, int count, u
         unsigned long long *e = B.peer[threadIdx.x] + BOARD_WORDS + B.rank;
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(e), "l"(epoch) : "memory");
         const unsigned long long *w = B.peer[B.rank] + BOARD_WORDS + threadIdx.x;
-        unsigned long long v = 0;
-        long long t0 = clock64();
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
-            if (clock64() - t0 > 20000000000ll) __trap();      // ~10 s: a rank died
-        } while (v < epoch);
+        svl_spin_ge(w, epoch, B.sg);
     }
     __syncthreads();
     const unsigned long long *own = B.peer[B.rank] + (size_t)par * SVL_MAX_RANKS * SVL_MAX_SWEEPS + first;
@@ -304,12 +295,7 @@ k_board_allsum(BoardArgs B, double *vals, int count, unsigned long long epoch) {
         unsigned long long *e = B.peer[threadIdx.x] + BOARD_WORDS + B.rank;
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(e), "l"(epoch) : "memory");
         const unsigned long long *w = B.peer[B.rank] + BOARD_WORDS + threadIdx.x;
-        unsigned long long v = 0;
-        long long t0 = clock64();
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
-            if (clock64() - t0 > 20000000000ll) __trap();
-        } while (v < epoch);
+        svl_spin_ge(w, epoch, B.sg);
     }
     __syncthreads();
     const unsigned long long *own = B.peer[B.rank] + (size_t)par * SVL_MAX_RANKS * SVL_MAX_SWEEPS;
@@ -326,7 +312,7 @@ int svl_board_allsum(svl_ctx *c, double *dvals, int count) {
     BoardArgs B;
     memset(&B, 0, sizeof(B));
     for (int r = 0; r < c->board_world; r++) B.peer[r] = c->board_peer[r];
-    B.rank = c->board_rank; B.world = c->board_world;
+    B.rank = c->board_rank; B.world = c->board_world; B.sg = svl_spin_guard(c);
     c->board_epoch += 1;
     k_board_allsum<<<1, 64, 0, c->stream>>>(B, dvals, count, c->board_epoch);
     SVL_CHECK(cudaGetLastError());
@@ -337,7 +323,7 @@ int svl_board_allmax(svl_ctx *c, int first, int count) {
     BoardArgs B;
     memset(&B, 0, sizeof(B));
     for (int r = 0; r < c->board_world; r++) B.peer[r] = c->board_peer[r];
-    B.rank = c->board_rank; B.world = c->board_world;
+    B.rank = c->board_rank; B.world = c->board_world; B.sg = svl_spin_guard(c);
     c->board_epoch += 1;
     k_board_allmax<<<1, 256, 0, c->stream>>>(B, c->d_resid, first, count, c->board_epoch);
     SVL_CHECK(cudaGetLastError());

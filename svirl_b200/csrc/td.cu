@@ -227,6 +227,7 @@ static int read_resid(svl_ctx *c, int first, int count) {
     SVL_CHECK(cudaMemcpyAsync(c->h_resid + first, c->d_resid + first, (size_t)count * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, c->stream));
     SVL_CHECK(cudaStreamSynchronize(c->stream));
+    SVL_TRY(svl_peer_error(c));
     if (!board && c->reduce_max_u64 && !c->reduce_max_dev) c->reduce_max_u64(c->h_resid + first, count);
     return 0;
 }

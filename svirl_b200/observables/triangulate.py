@@ -50,8 +50,8 @@ def triangulate(cells, psi, a, b, a_ai, b_bi, H, dx, dy, Nxc, rows0=0, dtype=np.
     j = (jg - np.int32(rows0)).astype(np.int32)          # local row: indexes the band
     ip, jp = i + 1, j + 1
     pi = np.pi
-    theta = np.angle(psi)
-    t_00, t_p0, t_pp, t_0p = theta[i, j], theta[ip, j], theta[ip, jp], theta[i, jp]
+    # np.angle at the candidate corners only (elementwise: same values as np.angle(psi)[...])
+    t_00, t_p0, t_pp, t_0p = np.angle(psi[i, j]), np.angle(psi[ip, j]), np.angle(psi[ip, jp]), np.angle(psi[i, jp])
     v = - (0.5 / pi) * (
         np.mod(t_p0 - t_00 - dx * a[i, j] + pi, 2.0 * pi)
         + np.mod(t_pp - t_p0 - dy * b[ip, j] + pi, 2.0 * pi)

@@ -39,6 +39,10 @@ def _lines_cross(p1, p2, q1, q2):
     return np.nan, np.nan, ph
 
 
+# above this many candidate cells the per-candidate arithmetic runs on whole arrays (triangulate.py)
+VECTOR_THRESHOLD = 4096
+
+
 class VortexDetector(object):
 
     def __init__(self, _vars, params, solver):
@@ -80,12 +84,11 @@ class VortexDetector(object):
                 ai, bi = self.fixed_vortices.irregular_vector_potential
                 a_ai, b_bi = a + ai, b + bi
             psi = self.vars.order_parameter
-            theta = np.angle(psi)
             dx, dy, pi = cfg.dx, cfg.dy, np.pi
             H = self.params.homogeneous_external_field
             found = []
             cand = self._candidates()
-            if cand.size > 4096:
+            if cand.size > VECTOR_THRESHOLD:
                 # many vortices: the same arithmetic on whole arrays (bit-identical, tests/test_triangulate_host.py)
                 from .triangulate import triangulate
                 tx, ty, tv = triangulate(cand, psi, a, b, a_ai, b_bi, H, dx, dy, cfg.Nxc, 0, cfg.dtype)
@@ -96,7 +99,10 @@ class VortexDetector(object):
             for n in cand:
                 i, j = self.unflatten_c(int(n))   # np.int32 like the reference: dx*i promotes to float64
                 ip, jp = i + 1, j + 1
-                t_00, t_p0, t_pp, t_0p = theta[i, j], theta[ip, j], theta[ip, jp], theta[i, jp]
+                # theta = np.angle(psi) at the four corners only (the reference takes it over the whole grid,
+                # vortex_detector.py:50; elementwise, so the values are the same)
+                t_00, t_p0, t_pp, t_0p = (np.angle(psi[i, j]), np.angle(psi[ip, j]), np.angle(psi[ip, jp]),
+                                          np.angle(psi[i, jp]))
                 v = - (0.5 / pi) * (
                     np.mod(t_p0 - t_00 - dx * a[i, j] + pi, 2.0 * pi)
                     + np.mod(t_pp - t_p0 - dy * b[ip, j] + pi, 2.0 * pi)

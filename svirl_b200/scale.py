@@ -22,35 +22,75 @@ import numpy as np
 from svirl_b200 import _lib
 from svirl_b200.parallel.slab import partition_rows
 
-_CHUNK = 1 << 24          # draws per chunk of the Mersenne-Twister stream
+class _MTStream(object):
+    """numpy's legacy Mersenne-Twister double stream (RandomState(seed).random_sample), walked by the library's C
+    helper svl_mt19937_doubles: same recurrence on the state numpy seeded, so the values are bit-identical, at ~2 ns
+    per draw instead of ~15 (and the GIL is released, so two streams advance concurrently)."""
+
+    def __init__(self, seed, skip=0):
+        st = np.random.RandomState(seed).get_state()
+        assert st[0] == "MT19937"
+        self.key = np.ascontiguousarray(st[1], dtype=np.uint32)
+        self.pos = C.c_int(int(st[2]))
+        self._pending_skip = int(skip)
+
+    def draw(self, n, out=None):
+        if out is None or out.size != int(n):
+            out = np.empty(int(n), dtype=np.float64)
+        _lib.call("svl_mt19937_doubles", self.key.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(self.pos),
+                  self._pending_skip, out.ctypes.data_as(C.POINTER(C.c_double)), int(n))
+        self._pending_skip = 0
+        return out
 
 
 class SeededPsi(object):
     """Walks the reference's random initial order parameter row band by row band, starting at row r0.
     psi[n] = (1 - level*u1[n]) * exp(i*pi*level*(2*u2[n] - 1)), u1 = draws [0, N), u2 = draws [N, 2N) of the
     legacy Mersenne Twister seeded with `seed` (np.random.seed + two np.random.rand(N) calls in the reference):
-    two generators are positioned at Nx*r0 and N + Nx*r0 once, then advance together."""
+    two streams are positioned at Nx*r0 and N + Nx*r0 once, then advance together."""
 
     def __init__(self, Nx, Ny, r0, seed, level=1.0, dtype=np.float64):
         self.Nx, self.level = int(Nx), level
         self.ctype = np.complex64 if np.dtype(dtype) == np.float32 else np.complex128
-        self.rs1, self.rs2 = np.random.RandomState(seed), np.random.RandomState(seed)
-        self._skip(self.rs1, self.Nx * int(r0))
-        self._skip(self.rs2, self.Nx * int(Ny) + self.Nx * int(r0))
+        self.s1 = _MTStream(seed, self.Nx * int(r0))
+        self.s2 = _MTStream(seed, self.Nx * int(Ny) + self.Nx * int(r0))
+        self._pool = None
+        self._free = []          # draw buffers handed back by transform() (first touch of fresh pages is not free)
 
-    @staticmethod
-    def _skip(rs, k):
-        while k > 0:
-            m = min(k, _CHUNK)
-            rs.random_sample(m)
-            k -= m
-
-    def next_rows(self, nrows):
+    def draws(self, nrows):
+        """(u1, u2) of the next `nrows` rows; the two streams are walked on two threads."""
         n = self.Nx * int(nrows)
-        u1, u2 = self.rs1.random_sample(n), self.rs2.random_sample(n)
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=2)
+        b1 = self._free.pop() if self._free else None
+        b2 = self._free.pop() if self._free else None
+        f2 = self._pool.submit(self.s2.draw, n, b2)
+        u1 = self.s1.draw(n, b1)
+        return u1, f2.result()
+
+    def transform(self, u1, u2, nrows):
+        """The reference's expression (vars.py:106), numpy ufuncs on the same values -> identical bits."""
         modulus = 1.0 - self.level * u1
         phase = self.level * 1.0j * np.pi * (2.0 * u2 - 1.0)
-        return (modulus * np.exp(phase)).astype(self.ctype).reshape(int(nrows), self.Nx).T      # [i, row]
+        out = (modulus * np.exp(phase)).astype(self.ctype).reshape(int(nrows), self.Nx).T      # [i, row]
+        self._free.append(u1)
+        self._free.append(u2)
+        return out
+
+    def transform_rows(self, u1, u2, nrows):
+        """Same values as transform() (bit for bit, tests/test_scale_host.py) through the library's host helper
+        svl_seeded_psi: no array temporaries, GIL released.  -> C-contiguous (nrows, Nx) array, x fastest."""
+        out = np.empty((int(nrows), self.Nx), dtype=self.ctype)
+        _lib.call("svl_seeded_psi", u1.ctypes.data_as(C.POINTER(C.c_double)), u2.ctypes.data_as(C.POINTER(C.c_double)),
+                  u1.size, float(self.level), out.ctypes.data_as(C.c_void_p), int(np.dtype(self.ctype).itemsize))
+        self._free.append(u1)
+        self._free.append(u2)
+        return out
+
+    def next_rows(self, nrows):
+        u1, u2 = self.draws(nrows)
+        return self.transform(u1, u2, nrows)
 
 
 def seeded_psi_rows(Nx, Ny, r0, r1, seed, level=1.0, dtype=np.float64):
@@ -109,11 +149,33 @@ class ScaleTD(object):
         _lib.call("svl_alloc", self._ctx, _lib.EDGE, 0, 0, C.byref(self.ab))
         # initial fields, band by band, halo rows included (so no exchange is needed before the first step)
         lo, hi = max(self.j0 - 8, 0), min(self.j1 + 8, self.Ny)
+        # the Mersenne-Twister streams are walked sequentially (C helper); the complex exponentials of a band -- the
+        # expensive part -- are evaluated on worker threads (svl_seeded_psi, GIL released) while the streams run
+        # ahead; uploads happen in band order on this thread
+        import os
+        from collections import deque
+        from concurrent.futures import ThreadPoolExecutor
         gen = SeededPsi(self.Nx, self.Ny, lo, random_seed, random_level, self.dtype)
+        nthreads = max(1, min(32, (os.cpu_count() or 2) - 2))
+        pool = ThreadPoolExecutor(max_workers=nthreads)
+        pending = deque()
+
+        def _upload(r, r1, fut):
+            band = fut.result()
+            _lib.call("svl_h2d_rows", self._ctx, self.psi, 0, r, r1, band.ctypes.data_as(C.c_void_p))
+
         for r in range(lo, hi, band_rows):
             r1 = min(r + band_rows, hi)
-            band = np.ascontiguousarray(gen.next_rows(r1 - r).T)                 # rows x Nx, x fastest
-            _lib.call("svl_h2d_rows", self._ctx, self.psi, 0, r, r1, band.ctypes.data_as(C.c_void_p))
+            u1, u2 = gen.draws(r1 - r)
+            pending.append((r, r1, pool.submit(gen.transform_rows, u1, u2, r1 - r)))
+            del u1, u2
+            while len(pending) > 2 * nthreads:
+                _upload(*pending.popleft())
+        while pending:
+            _upload(*pending.popleft())
+        pool.shutdown()
+        for r in range(lo, hi, band_rows):
+            r1 = min(r + band_rows, hi)
             a, b = symmetric_gauge_rows(self.Nx, self.Ny, dx, dy, homogeneous_external_field, r, r1, self.dtype)
             fa = np.ascontiguousarray(a.T)
             _lib.call("svl_h2d_rows", self._ctx, self.ab, 0, r, r1, fa.ctypes.data_as(C.c_void_p))

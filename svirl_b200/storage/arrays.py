@@ -110,7 +110,9 @@ class DeviceArray(object):
     def get(self):
         """Flat host copy in the reference's device layout."""
         self._check()
-        out = np.empty(self.size, dtype=self.dtype)
+        # zeros, not empty: on a slab context svl_d2h fills the owned rows only, and a later push() must not
+        # upload uninitialised memory into the halo rows (only GLSolver.owned_rows() are valid on slabs)
+        out = np.zeros(self.size, dtype=self.dtype)
         _lib.call("svl_d2h", self.par.ctx, out.ctypes.data_as(C.c_void_p), self.handle)
         return out
 

@@ -12,14 +12,27 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+# a dead peer must fail a slab test, not hang the GPU box (the library's default is to wait forever)
+os.environ.setdefault("SVL_SPIN_TIMEOUT_MS", "20000")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def _parse_meta(text):
+    """Fixture metadata is the repr of a dict of plain values; `inf` / `nan` appear bare."""
+    import ast
+    import re
+    text = re.sub(r"(?<![\w.'\"])(-?)inf(?![\w'\"])", r"\g<1>1e999", text)     # literal_eval reads 1e999 as float inf
+    text = re.sub(r"(?<![\w.'\"])nan(?![\w'\"])", "None", text)
+    return ast.literal_eval(text)
 
 
 def load_golden(name):
     d = dict(np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False))
     if "meta" in d:
-        d["meta"] = eval(str(d["meta"]), {"inf": np.inf, "nan": np.nan})
+        d["meta"] = _parse_meta(str(d["meta"]))
     return d
 
 
