@@ -114,3 +114,30 @@ def test_cfg3_full_size_against_reference_on_gpu():
     assert relerr(o["psi"], r["psi"]) < 1e-10
     assert relerr(o["a"], r["a"]) < 1e-10 and relerr(o["b"], r["b"]) < 1e-10
     assert abs(o["E_td"] - r["E_td"]) < 1e-10 * abs(r["E_td"])
+
+
+def test_cfg4_cg_follows_reference_until_the_reference_diverges():
+    """BASELINE configs[3] at 8192^2 (kappa 2, fp64, 20 TDGL steps, then CG).  The fixture holds what the UNMODIFIED
+    reference did on a B200 (tools/cfg4_adjudicate.py, profiles/r02_cfg4_adjudicate_8192.json): its 4th SciPy BFGS
+    line search returns alpha ~ -1e142 and the state is lost (E = inf, then NaN).  This library must reproduce the
+    reference's energies while the reference is finite, and -- with the rescue of solvers/cg.py -- keep descending."""
+    import json
+    from svirl_b200 import GLSolver
+    with open(os.path.join(ROOT, "tests", "golden", "cfg4_reference_cg_8192.json")) as f:
+        fx = json.load(f)
+    Er = np.array(fx["reference_energies"])
+    nfin = int(np.argmin(np.isfinite(Er))) if not np.isfinite(Er).all() else len(Er)
+    assert nfin == 3                                     # the reference survives three iterations
+    c = fx["config"]
+    gl = GLSolver(Nx=c["Nx"], Ny=c["Ny"], dx=c["dx"], dy=c["dy"], dtype=np.float64, gl_parameter=c["gl_parameter"],
+                  normal_conductivity=c["normal_conductivity"], homogeneous_external_field=c["homogeneous_external_field"],
+                  random_seed=c["random_seed"])
+    gl.solve.td(dt=0.1, Nt=fx["td_steps"])
+    gl.solve._init_cg()
+    gl.solve._cg._CG__convergence_rtol = -1.0
+    gl.solve.cg(n_iter=8)
+    E = np.array(gl.solve._cg.cg_energies, dtype=np.float64)
+    assert np.allclose(E[:nfin], Er[:nfin], rtol=1e-8)
+    assert np.all(np.isfinite(E)) and np.all(np.diff(E) < 0)
+    assert gl.solve._cg.line_search_rescues >= 1
+    gl.par.close()
