@@ -267,8 +267,9 @@ def bench_cg(args, wl, gl, par, N):
     region because it is part of an iteration."""
     from svirl_b200 import _lib
     gl.solve.td(dt=0.1, Nt=20)
-    if N >= 8192 * 8192:
-        gl.cfg.cg_line_search = "normalized"           # SciPy BFGS runs away on raw coefficients of this size
+    if args.line_search:
+        gl.cfg.cg_line_search = args.line_search        # default "reference": SciPy BFGS as in the reference, redone on the
+                                                        # normalised polynomial only when it runs away (rescues are counted)
     gl.cfg.convergence_rtol = 0.0
     gl.solve._init_cg()
     gl.solve._cg._CG__convergence_rtol = -1.0          # never stop early: time exactly K iterations
@@ -434,6 +435,7 @@ def main():
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (svl_set_option)")
     ap.add_argument("--ny-mult", type=int, default=1, help="multiply Ny (to run an N-GPU weak-scaling grid on fewer GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--line-search", default=None, choices=[None, "reference", "normalized"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -56,7 +56,9 @@ int svl_synchronize(svl_ctx *ctx);
 /* knobs: "psi_kernel" (0 = plain per-node, 1 = temporally blocked streaming, 2 = register-resident
  * tile kernel, default), "psi_k" (psi sweeps fused per launch), "tma" (0/1), "graphs" (0/1),
  * "a_kernel" (0 = per-node A sweep, 1..4 = tile kernel fusing sweep pairs in four layouts, default 2),
- * "cg_fused" (1 = three-pass CG iteration, default; 0 = composition of the single kernels) */
+ * "cg_fused" (2 = two-pass CG iteration svl_cg_pass_a/_b, default where it applies; 1 = three-pass iteration
+ * svl_cg_begin/_end; 0 = composition of the single kernels), "spin_timeout_ms" (bound of the spin waits on peer
+ * GPUs, 0 = wait forever, default; env SVL_SPIN_TIMEOUT_MS) */
 int svl_set_option(svl_ctx *ctx, const char *name, int value);
 int svl_get_stat(svl_ctx *ctx, const char *name, double *value);
 /* self-test hook: the library's own sincos (used for every link variable exp(-i d A)) on n values */
@@ -170,6 +172,22 @@ int svl_cg_begin(svl_ctx *ctx, int solveA, int have_prev, double kappa2, double 
 int svl_cg_end(svl_ctx *ctx, int solveA, double kappa2, double eps, const svl_buf *eps_field, double H,
                svl_buf *psi, const svl_buf *abei, svl_buf *ab, const svl_buf *d_psi, const svl_buf *d_A,
                double alpha_psi, double alpha_A, double *E_out);
+
+/* Two-pass CG iteration (36R+2 bytes per node, the fused lower bound of the path; single GPU, no external potential):
+ *  svl_cg_pass_a: [do_update: psi += alpha_psi*d_psi, ab += alpha_A*d_A, free energy of the new state -> E_out]
+ *                 [do_grad: Jacobians at the (new) state -> g_psi, g_A IN PLACE (on entry they hold the previous
+ *                  gradient when have_prev); have_prev: PR+ beta from the four sums -> beta_inout (also kept on the
+ *                  device for pass b); otherwise beta_inout is taken as is (quirk Q6: beta persists across cg() calls)]
+ *  svl_cg_pass_b: d <- beta*d - g; 17 (solveA) or 5 coefficients of the line-search polynomial -> c_out.
+ * One iteration of svirl/solvers/cg.py:477-544 = pass_b, host line search, pass_a; the first pass_a of a cg() call
+ * has do_update = 0, the last one may have do_grad = 0. */
+int svl_cg_pass_a(svl_ctx *ctx, int solveA, int do_update, int do_grad, int have_prev, double kappa2, double eps,
+                  const svl_buf *eps_field, double H, svl_buf *psi, const svl_buf *abei, svl_buf *ab,
+                  const svl_buf *d_psi, const svl_buf *d_A, double alpha_psi, double alpha_A, svl_buf *g_psi,
+                  svl_buf *g_A, double *beta_inout /* [2] */, double *E_out);
+int svl_cg_pass_b(svl_ctx *ctx, int solveA, double kappa2, double eps, double H, const svl_buf *psi,
+                  const svl_buf *abei, const svl_buf *ab, const svl_buf *g_psi, const svl_buf *g_A, svl_buf *d_psi,
+                  svl_buf *d_A, double *c_out);
 
 /* ---- observables (svirl/cuda/observables.h:5-235) -------------------------------------- */
 int svl_magnetic_field(svl_ctx *ctx, const svl_buf *abei, const svl_buf *ab, svl_buf *B_out);

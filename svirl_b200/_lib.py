@@ -56,6 +56,8 @@ SIGNATURES = {
     "svl_axpy": ([_p, _p, _p, _p, _d], _i),
     "svl_cg_begin": ([_p, _i, _i, _d, _d, _p, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _pd, _pd], _i),
     "svl_cg_end": ([_p, _i, _d, _d, _p, _d, _p, _p, _p, _p, _p, _d, _d, _pd], _i),
+    "svl_cg_pass_a": ([_p, _i, _i, _i, _i, _d, _d, _p, _d, _p, _p, _p, _p, _p, _d, _d, _p, _p, _pd, _pd], _i),
+    "svl_cg_pass_b": ([_p, _i, _d, _d, _d, _p, _p, _p, _p, _p, _p, _p, _pd], _i),
     "svl_magnetic_field": ([_p, _p, _p, _p], _i),
     "svl_current_density": ([_p, _d, _d, _p, _p, _p], _i),
     "svl_supercurrent_density": ([_p, _p, _p, _p, _p], _i),

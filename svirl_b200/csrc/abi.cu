@@ -106,7 +106,7 @@ extern "C" int svl_create(svl_ctx **out, int device_id, int Nx, int Ny, double d
     c->opt_tma = 1;
     c->opt_graphs = 1;
     c->opt_a_kernel = 2;
-    c->opt_cg_fused = 1;
+    c->opt_cg_fused = 2;
     c->opt_resid_board = 1;
     c->opt_slab_split = 1;
     c->pred_psi = c->pred_A = c->pred_psi2 = c->pred_A2 = 0;
@@ -202,6 +202,8 @@ extern "C" int svl_set_option(svl_ctx *c, const char *name, int v) {
 extern "C" int svl_get_stat(svl_ctx *c, const char *name, double *v) {
     SVL_REQUIRE(c && name && v, "null argument");
     if (!strcmp(name, "launches")) *v = c->stat_launches;
+    else if (!strcmp(name, "cg_fused")) *v = c->opt_cg_fused;
+    else if (!strcmp(name, "slab_on")) *v = c->slab_on;
     else if (!strcmp(name, "replays")) *v = c->stat_replays;
     else if (!strcmp(name, "psi_sweeps")) *v = c->stat_psi_sweeps;
     else if (!strcmp(name, "A_sweeps")) *v = c->stat_A_sweeps;

@@ -1,9 +1,11 @@
 """Modified nonlinear conjugate-gradient minimiser (API of svirl/solvers/cg.py:12-558).
 
-Device work per iteration is two library calls (svl_cg_begin: Jacobians, PR+ beta, direction
-update, line-search coefficients; svl_cg_end: variable update + free energy); the line search
-itself stays on the host and is the reference's numpy/scipy call, unchanged, because the
-trajectory depends on it bit by bit (cg.py:227-235, 378-419).
+Device work per iteration is two library calls and two passes over HBM (svl_cg_pass_b: direction
+update + line-search coefficients; svl_cg_pass_a: variable update + free energy + the Jacobians of
+the NEXT iteration + its PR+ beta); with an external potential or on row slabs the three-pass pair
+svl_cg_begin / svl_cg_end is used instead.  The line search itself stays on the host and is the
+reference's numpy/scipy call, unchanged, because the trajectory depends on it bit by bit
+(cg.py:227-235, 378-419).
 
 State that persists across cg() calls exactly as in the reference (quirk Q6): beta_psi,
 beta_A and, for finite kappa, the search directions."""
@@ -159,14 +161,58 @@ class CG(object):
         return self._cg_alpha_min_scaled()
 
     # ---- the two minimisation loops
+    def _line_search(self, cbuf, solveA):
+        r = np.array(cbuf[:], dtype=cfg.dtype)
+        if solveA:
+            self._store_c17(r)
+            return self._cg_alpha_min_guarded()
+        self.__c[:] = r
+        return self._cg_alpha_psi_min(), 0.0
+
+    def _iterate_two_pass(self, n_iter, solveA, s):
+        """One iteration = svl_cg_pass_b (d <- beta d - g, coefficients), host line search, svl_cg_pass_a (update,
+        energy, and -- unless this is the last iteration -- the gradient and PR+ beta of the next one).  Same
+        arithmetic and the same order of operations on the state as svirl/solvers/cg.py:477-544; the gradient of
+        iteration i+1 is merely evaluated in the pass that produces its state."""
+        ctx = self.par.ctx
+        dA = self.__gdir_A if solveA else None
+        gA = self.__gjac_A if solveA else None
+        beta = (C.c_double * 2)(self._beta_psi, self._beta_A)
+        cbuf = (C.c_double * (17 if solveA else 5))()
+        E = C.c_double()
+        # gradient at the initial state; beta stays what the previous cg() call left (quirk Q6)
+        _lib.call("svl_cg_pass_a", ctx, int(solveA), 0, 1, 0, s['k2'], s['eps'], s['epsf'], s['H'], s['psi'], None, s['ab'],
+                  self.__gdir_psi.handle, _h(dA), 0.0, 0.0, self.__gjac_psi.handle, _h(gA), beta, C.byref(E))
+        for i in range(n_iter):
+            _lib.call("svl_cg_pass_b", ctx, int(solveA), s['k2'], 0.0 if s['epsf'] is not None else s['eps'], s['H'],
+                      s['psi'], None, s['ab'], self.__gjac_psi.handle, _h(gA), self.__gdir_psi.handle, _h(dA), cbuf)
+            alpha_psi, alpha_A = self._line_search(cbuf, solveA)
+            last = i == n_iter - 1
+            kept = (beta[0], beta[1])
+            _lib.call("svl_cg_pass_a", ctx, int(solveA), 1, int(not last), 1, s['k2'], s['eps'], s['epsf'], s['H'], s['psi'],
+                      None, s['ab'], self.__gdir_psi.handle, _h(dA), float(cfg.dtype(alpha_psi)), float(cfg.dtype(alpha_A)),
+                      self.__gjac_psi.handle, _h(gA), beta, C.byref(E))
+            self.cg_energies.append(cfg.dtype(E.value))
+            if i > 0 and np.abs(self.cg_energies[i] / self.cg_energies[i - 1] - 1.0) < self.__convergence_rtol:
+                beta[0], beta[1] = kept          # the reference stops before it would compute the next beta (quirk Q6)
+                break
+        return beta
+
     def _iterate(self, n_iter, solveA):
         s = self._state()
         ctx = self.par.ctx
         self.cg_energies = []
-        nul = None
-        gA, gAp, dA = ((self.__gjac_A, self.__gjac_A_prev, self.__gdir_A) if solveA else (nul, nul, nul))
         if not solveA:
             self.__gdir_psi.fill(0.0)            # the kappa=inf loop restarts from steepest descent (cg.py:264)
+        if s['abei'] is None and int(self.par.stat("cg_fused")) >= 2 and not int(self.par.stat("slab_on")) and n_iter > 0:
+            beta = self._iterate_two_pass(n_iter, solveA, s)
+            self._beta_psi, self._beta_A = beta[0], beta[1]
+            self.vars._psi.need_dtoh_sync()
+            if solveA:
+                self.vars._vp.need_dtoh_sync()
+            return
+        nul = None
+        gA, gAp, dA = ((self.__gjac_A, self.__gjac_A_prev, self.__gdir_A) if solveA else (nul, nul, nul))
         beta = (C.c_double * 2)(self._beta_psi, self._beta_A)
         ncoef = 17 if solveA else 5
         cbuf = (C.c_double * ncoef)()
@@ -175,13 +221,7 @@ class CG(object):
             _lib.call("svl_cg_begin", ctx, int(solveA), int(i > 0), s['k2'], s['eps'], s['epsf'], s['H'], s['psi'],
                       s['abei'], s['ab'], self.__gjac_psi.handle, self.__gjac_psi_prev.handle,
                       self.__gdir_psi.handle, _h(gA), _h(gAp), _h(dA), beta, cbuf)
-            r = np.array(cbuf[:], dtype=cfg.dtype)
-            if solveA:
-                self._store_c17(r)
-                alpha_psi, alpha_A = self._cg_alpha_min_guarded()
-            else:
-                self.__c[:] = r
-                alpha_psi, alpha_A = self._cg_alpha_psi_min(), 0.0
+            alpha_psi, alpha_A = self._line_search(cbuf, solveA)
             _lib.call("svl_cg_end", ctx, int(solveA), s['k2'], s['eps'], s['epsf'], s['H'], s['psi'], s['abei'],
                       s['ab'], self.__gdir_psi.handle, _h(dA), float(cfg.dtype(alpha_psi)),
                       float(cfg.dtype(alpha_A)), C.byref(E))

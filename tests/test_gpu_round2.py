@@ -91,3 +91,47 @@ def test_jacobi_diagonal_vanishes_on_inactive_nodes(shape, dtype, kernel):
     act[:-1, :-1] |= mt; act[1:, :-1] |= mt; act[:-1, 1:] |= mt; act[1:, 1:] |= mt
     assert np.all(psi[~act] == 0)
     gl.par.close()
+
+
+@pytest.mark.parametrize("shape", [(300, 270), (517, 700), (70, 40), (249, 65), (8, 5)], ids=lambda s: "%dx%d" % s)
+@pytest.mark.parametrize("case", ["f64_k2_eps", "f64_kinf", "f32_k2", "f32_kinf"])
+def test_cg_two_pass_iteration_equals_kernel_composition(case, shape):
+    """The two-pass CG iteration (cg_pipe.cu: update + energy + next Jacobians + PR sums / direction + coefficients)
+    against the composition of the single kernels (option cg_fused = 0; those are checked one by one against the
+    reference in test_kernels), on strip-boundary and ragged sizes: same energies and state to rounding over two
+    cg() calls (quirk Q6: beta and, for finite kappa, the directions persist), the second one ending by convergence."""
+    from svirl_b200 import GLSolver
+    dtype = np.float64 if case.startswith("f64") else np.float32
+    Nx, Ny = shape
+    rs = np.random.RandomState(Nx + Ny)
+    kw = dict(Nx=Nx, Ny=Ny, dx=0.5, dy=0.4, dtype=dtype, homogeneous_external_field=0.1, random_seed=7,
+              gl_parameter=np.inf if "kinf" in case else 2.0, normal_conductivity=10.0,
+              material_tiling=rs.rand(Nx - 1, Ny - 1) > 0.1)
+    if "eps" in case:
+        kw["linear_coefficient"] = (0.7 + 0.3 * rs.rand(Nx, Ny)).astype(dtype)
+    res = []
+    for fused in (0, 2):
+        gl = GLSolver(**kw)
+        gl.par.set_option("cg_fused", fused)
+        gl.solve.td(dt=0.1, Nt=5)
+        gl.solve.cg(n_iter=4)
+        E1 = np.array(gl.solve._cg.cg_energies, dtype=np.float64)
+        gl.cfg.convergence_rtol = 0.5
+        gl.solve._cg._CG__convergence_rtol = 0.5          # stops after the second iteration (i = 1)
+        gl.solve.cg(n_iter=5)
+        E2 = np.array(gl.solve._cg.cg_energies, dtype=np.float64)
+        gl.solve._cg._CG__convergence_rtol = -1.0
+        gl.solve.cg(n_iter=2)
+        E3 = np.array(gl.solve._cg.cg_energies, dtype=np.float64)
+        a, b = gl.vars.vector_potential
+        res.append((E1, E2, E3, gl.vars.order_parameter, a.copy(), b.copy()))
+        gl.par.close()
+    f64 = dtype is np.float64
+    assert len(res[0][1]) == len(res[1][1]) == 2
+    rt = (1e-8 if "kinf" not in case else 1e-11) if f64 else 3e-4
+    at = rt * np.abs(res[0][0]).max()
+    for k in (0, 1, 2):
+        assert np.allclose(res[0][k], res[1][k], rtol=rt, atol=at), (k, res[0][k], res[1][k])
+    tol = (1e-7 if "kinf" not in case else 1e-10) if f64 else 3e-3
+    for k in (3, 4, 5):
+        assert np.abs(res[0][k] - res[1][k]).max() < tol
