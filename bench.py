@@ -435,7 +435,7 @@ def main():
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (svl_set_option)")
     ap.add_argument("--ny-mult", type=int, default=1, help="multiply Ny (to run an N-GPU weak-scaling grid on fewer GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--line-search", default=None, choices=[None, "reference", "normalized"])
+    ap.add_argument("--line-search", default=None, choices=[None, "reference", "normalized", "native"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -189,6 +189,11 @@ int svl_cg_pass_b(svl_ctx *ctx, int solveA, double kappa2, double eps, double H,
                   const svl_buf *abei, const svl_buf *ab, const svl_buf *g_psi, const svl_buf *g_A, svl_buf *d_psi,
                   svl_buf *d_A, double *c_out);
 
+/* Opt-in host line search (replaces scipy.optimize.minimize(BFGS) of svirl/solvers/cg.py:378-419 and
+ * the polyroots call of :227-235 when cfg.cg_line_search = 'native'): minimum of the coefficient polynomial in the
+ * basin of (0, 0) by damped Newton on c / max|c|.  c: 17 (solveA) or 5 coefficients in the kernels' order. */
+int svl_cg_line_search(const double *c, int solveA, double *alpha_out /* [2] */, int *iters_out);
+
 /* ---- observables (svirl/cuda/observables.h:5-235) -------------------------------------- */
 int svl_magnetic_field(svl_ctx *ctx, const svl_buf *abei, const svl_buf *ab, svl_buf *B_out);
 int svl_current_density(svl_ctx *ctx, double kappa2, double H, const svl_buf *abei, const svl_buf *ab,

@@ -58,6 +58,7 @@ SIGNATURES = {
     "svl_cg_end": ([_p, _i, _d, _d, _p, _d, _p, _p, _p, _p, _p, _d, _d, _pd], _i),
     "svl_cg_pass_a": ([_p, _i, _i, _i, _i, _d, _d, _p, _d, _p, _p, _p, _p, _p, _d, _d, _p, _p, _pd, _pd], _i),
     "svl_cg_pass_b": ([_p, _i, _d, _d, _d, _p, _p, _p, _p, _p, _p, _p, _pd], _i),
+    "svl_cg_line_search": ([_pd, _i, _pd, C.POINTER(_i)], _i),
     "svl_magnetic_field": ([_p, _p, _p, _p], _i),
     "svl_current_density": ([_p, _d, _d, _p, _p, _p], _i),
     "svl_supercurrent_density": ([_p, _p, _p, _p, _p], _i),

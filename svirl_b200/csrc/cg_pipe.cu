@@ -13,16 +13,16 @@
 // line search (svirl/solvers/cg.py:227-235, 378-419) sits between B and A exactly as in the reference.
 //
 // Data movement (the point of this file; the three-pass kernels were latency bound at 0.4-0.6 of the HBM peak with
-// per-thread loads two rows ahead): a CTA owns a strip of <= 248 columns x L rows.  A producer warp streams the strip
+// per-thread loads two rows ahead): a CTA owns a strip of <= 217 columns x L rows.  A producer warp streams the strip
 // row by row into a ring of shared-memory stages with cp.async.bulk (TMA, one bulk copy per plane and row, completion
-// on an mbarrier): up to NS-1 rows of every plane are in flight per CTA without costing a register.  Eight consumer warps
+// on an mbarrier): up to NS-1 rows of every plane are in flight per CTA without costing a register.  Seven consumer warps
 // walk down the rows: a lane owns one column, keeps the rows y-1, y, y+1 of the (updated) state in registers (N/S
 // neighbours), takes the E/W neighbours from the stage, and evaluates each link variable exp(-i d A) once (the W link
 // comes from the neighbouring lane by shuffle; warps overlap by one column so no lane needs a second sincos).
 // Reductions accumulate in double per thread over the whole strip and are reduced once per CTA in a fixed order.
 #include "common.cuh"
 
-#define CGP_WARPS 8
+#define CGP_WARPS 7                        // consumer warps; + 1 producer warp = 256 threads, 2 CTAs x 128 registers per SM
 #define CGP_CONS (32 * CGP_WARPS)
 #define CGP_THREADS (CGP_CONS + 32)        // + one producer warp
 #define CGP_MAXPL 9
@@ -64,10 +64,10 @@ __device__ __forceinline__ void cgp_produce(const PipeGeom &G, unsigned char *st
     const int xs = x0 - G.HX + cut;
     uint32_t total = 0;
     for (int p = 0; p < G.nplanes; p++) total += (uint32_t)((G.NC - cut) * G.esize[p]);
-    int it = 0;
+    unsigned it = 0;
     for (int r = r_first; r <= r_last; r++, it++) {
-        const int s = it % NS;
-        if (it >= NS) cgp_wait(&empty[s], (uint32_t)((it / NS - 1) & 1));
+        const unsigned s = it & (NS - 1);
+        if (it >= NS) cgp_wait(&empty[s], (it / NS - 1) & 1);
         if (lane == 0)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cgp_u32(&full[s])), "r"(total) : "memory");
         __syncwarp();
@@ -82,42 +82,12 @@ __device__ __forceinline__ void cgp_produce(const PipeGeom &G, unsigned char *st
     }
 }
 
-template <typename R> __device__ __forceinline__ void cgp_du_w(unsigned f, R &wW, R &wE, R &wS, R &wN, R &gw) {
-    R mm = (f & NF_MM) ? (R)1 : (R)0, mp = (f & NF_MP) ? (R)1 : (R)0;
-    R pm = (f & NF_PM) ? (R)1 : (R)0, pp = (f & NF_PP) ? (R)1 : (R)0;
-    wW = (R)0.5 * (mm + mp); wE = (R)0.5 * (pm + pp);
-    wS = (R)0.5 * (mm + pm); wN = (R)0.5 * (mp + pp);
-    gw = (R)0.25 * (wW + wE + wS + wN);
-}
 // psi1 * U(ph) - psi0 with (s, c) = sincos(ph)   (cg.h:305-311)
 template <typename R, typename C> __device__ __forceinline__ C cgp_gradc(C p0, R s, R c, C p1) {
     C z;
     z.x = p1.x * c + p1.y * s - p0.x;
     z.y = p1.y * c - p1.x * s - p0.y;
     return z;
-}
-// curl-curl stencils with the boundary doubling of quirk Q10 (cg.h:176-217, 240-282), operands from registers
-template <typename R>
-__device__ __forceinline__ R cgp_curl_a(const Geo &g, int j, R H, R a0, R aS, R aN, R bS, R bSE, R b0, R bE) {
-    const R idy = (R)g.idy, idy2 = (R)g.idy2, idxy = (R)g.idxy;
-    R v = 0, dd = 1;
-    if (j == 0) { v -= (R)2.0 * H * idy; dd = 2; }
-    else if (j + 1 == g.Ny) { v += (R)2.0 * H * idy; dd = 2; }
-    v += (R)2.0 * idy2 * a0;
-    if (j > 0) v += dd * (-idy2 * aS + idxy * bS - idxy * bSE);
-    if (j + 1 < g.Ny) v += dd * (-idy2 * aN - idxy * b0 + idxy * bE);
-    return v;
-}
-template <typename R>
-__device__ __forceinline__ R cgp_curl_b(const Geo &g, int i, R H, R b0, R bW, R bE, R aW, R aWN, R a0, R aN) {
-    const R idx = (R)g.idx, idx2 = (R)g.idx2, idxy = (R)g.idxy;
-    R v = 0, dd = 1;
-    if (i == 0) { v += (R)2.0 * H * idx; dd = 2; }
-    else if (i + 1 == g.Nx) { v -= (R)2.0 * H * idx; dd = 2; }
-    v += (R)2.0 * idx2 * b0;
-    if (i > 0) v += dd * (-idx2 * bW + idxy * aW - idxy * aWN);
-    if (i + 1 < g.Nx) v += dd * (-idx2 * bE - idxy * a0 + idxy * aN);
-    return v;
 }
 
 template <typename R> struct CgpState {
@@ -126,15 +96,79 @@ template <typename R> struct CgpState {
     const uint8_t *nf;
 };
 
+// Stage layout, known at compile time (the consumers address every plane as base + immediate): row windows of NC
+// columns, each rounded up to 128 bytes, in the order the host adds the planes (cgp_add).
+template <typename R, int LOUT> struct PipeDims {
+    static constexpr int HX = sizeof(R) == 8 ? 2 : 4;
+    static constexpr int NC = (LOUT * CGP_WARPS + 2 * HX + 3) / 4 * 4;
+    static constexpr int RB = (NC * (int)sizeof(R) + 127) / 128 * 128;          // real plane
+    static constexpr int CB = (NC * 2 * (int)sizeof(R) + 127) / 128 * 128;      // complex plane
+};
+template <typename R, bool HAVEA, bool SOLVEA, bool PREVPL> struct LayoutA {     // psi, d, [a, b], [da, db], [g, ga, gb]
+    typedef PipeDims<R, 31> D;
+    static constexpr int o_psi = 0, o_d = D::CB, o_a = 2 * D::CB, o_b = o_a + (HAVEA ? D::RB : 0);
+    static constexpr int o_da = o_b + (HAVEA ? D::RB : 0), o_db = o_da + (SOLVEA ? D::RB : 0);
+    static constexpr int o_g = o_db + (SOLVEA ? D::RB : 0), o_ga = o_g + (PREVPL ? D::CB : 0);
+    static constexpr int o_gb = o_ga + (PREVPL && SOLVEA ? D::RB : 0), stage = o_gb + (PREVPL && SOLVEA ? D::RB : 0);
+};
+template <typename R, bool HAVEA, bool SOLVEA> struct LayoutB {                  // psi, g, d, [a, b], [ga, gb, da, db]
+    typedef PipeDims<R, 32> D;
+    static constexpr int o_psi = 0, o_g = D::CB, o_d = 2 * D::CB, o_a = 3 * D::CB, o_b = o_a + (HAVEA ? D::RB : 0);
+    static constexpr int o_ga = o_b + (HAVEA ? D::RB : 0), o_gb = o_ga + (SOLVEA ? D::RB : 0);
+    static constexpr int o_da = o_gb + (SOLVEA ? D::RB : 0), o_db = o_da + (SOLVEA ? D::RB : 0);
+    static constexpr int stage = o_db + (SOLVEA ? D::RB : 0);
+};
+
+// Per-flag weight table (16 entries, indexed by the node flag nibble): the DU weights of common.h:13 / cg.h:59-64
+// pre-multiplied by the constants they always meet.  w is 0, 1/2 or 1, so every product below is an exact scaling of the
+// grid constant and the kernels round exactly like the term-by-term expressions of the reference.
+enum { W_G = 0, W_G2, W_CW, W_CE, W_CS, W_CN, W_EE, W_EN, W_JE, W_JN, W_E3, W_N3, W_E12, W_N12, W_N };
+template <typename R> __device__ __forceinline__ void cgp_fill_lut(R *lut, const Geo &g) {
+    const int f = threadIdx.x;
+    if (f >= 16) return;
+    const R idx = (R)g.idx, idy = (R)g.idy, idx2 = (R)g.idx2, idy2 = (R)g.idy2;
+    const R mm = (f & NF_MM) ? (R)1 : (R)0, mp = (f & NF_MP) ? (R)1 : (R)0, pm = (f & NF_PM) ? (R)1 : (R)0, pp = (f & NF_PP) ? (R)1 : (R)0;
+    const R wW = (R)0.5 * (mm + mp), wE = (R)0.5 * (pm + pp), wS = (R)0.5 * (mm + pm), wN = (R)0.5 * (mp + pp);
+    const R gw = (R)0.25 * (wW + wE + wS + wN);
+    R *t = lut + f * W_N;
+    t[W_G] = gw; t[W_G2] = (R)2.0 * gw;
+    t[W_CW] = (R)-2.0 * (wW * idx2); t[W_CE] = (R)-2.0 * (wE * idx2); t[W_CS] = (R)-2.0 * (wS * idy2); t[W_CN] = (R)-2.0 * (wN * idy2);
+    t[W_EE] = wE * idx2; t[W_EN] = wN * idy2;
+    t[W_JE] = -wE * idx; t[W_JN] = -wN * idy;
+    t[W_E3] = -wE * (idx2 / (R)3.0); t[W_N3] = -wN * (idy2 / (R)3.0);
+    t[W_E12] = -wE * (idx2 / (R)12.0); t[W_N12] = -wN * (idy2 / (R)12.0);
+}
+
+// the two link variables of a node, branch-free; the out-of-range fallback (|phase| > 1e5) is taken by nobody in practice
+template <typename R> __device__ __forceinline__ void cgp_sincos2(R pa, R pb, R &sa, R &ca, R &sb, R &cb) {
+    sincos_fast(pa, &sa, &ca);
+    sincos_fast(pb, &sb, &cb);
+    if (!(sincos_fast_ok(pa) && sincos_fast_ok(pb))) { sincos_any(pa, &sa, &ca); sincos_any(pb, &sb, &cb); }
+}
+
+__device__ __forceinline__ void cgp_init_barriers(uint64_t *full, uint64_t *empty, int ns) {
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ns; s++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cgp_u32(&full[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cgp_u32(&empty[s])), "r"(CGP_WARPS));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+}
+
 // ============================================================================================ pass A
-// planes: 0 psi, 1 dpsi, [2 a, 3 b], [4 da, 5 db], gprev: psi then a, b
 template <typename R, bool HAVEA, bool SOLVEA, bool UPDATE, bool GRAD, bool PREV, int NS>
 __global__ void __launch_bounds__(CGP_THREADS, 2)
 k_cgp_a(const __grid_constant__ PipeGeom G, CgpState<R> S, R alpha_psi, R alpha_A,
         typename V2<R>::type *__restrict__ psi_out, R *__restrict__ a_out, R *__restrict__ b_out,
         typename V2<R>::type *__restrict__ gpsi, R *__restrict__ ga, R *__restrict__ gb, double *partials) {
     typedef typename V2<R>::type C;
+    typedef LayoutA<R, HAVEA, SOLVEA, GRAD && PREV> LY;
+    constexpr int HX = LY::D::HX;
+    static_assert((NS & (NS - 1)) == 0, "NS must be a power of two");
     extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ R lut[16 * W_N];
     uint64_t *full = (uint64_t *)smem, *empty = full + NS;
     unsigned char *stages = smem + 128;
     const Geo &g = G.g;
@@ -142,22 +176,14 @@ k_cgp_a(const __grid_constant__ PipeGeom G, CgpState<R> S, R alpha_psi, R alpha_
     const int cs = blockIdx.x % G.nstrips, rc = blockIdx.x / G.nstrips;
     const int x0 = cs * G.WS;
     const int ys = G.ylo + rc * G.L, ye = ys + G.L < G.yhi ? ys + G.L : G.yhi;
-    constexpr int P_PSI = 0, P_D = 1, P_A = 2, P_B = 3, P_DA = 4, P_DB = 5;
-    constexpr int P_GP = HAVEA ? (SOLVEA ? 6 : 4) : 2;
 
-    if (tid == 0) {
-        for (int s = 0; s < NS; s++) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cgp_u32(&full[s])));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cgp_u32(&empty[s])), "r"(CGP_WARPS));
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
+    cgp_init_barriers(full, empty, NS);
+    cgp_fill_lut<R>(lut, g);
     // first strip: the left halo columns are never filled (clamped copies); make them finite once
-    if (x0 - G.HX < 0) {
+    if (x0 - HX < 0) {
         for (int q = tid; q < NS * G.nplanes * 8; q += CGP_THREADS) {       // HX * esize <= 64 bytes = 8 doubles
             const int s = q / (G.nplanes * 8), p = (q / 8) % G.nplanes, e = q % 8;
-            if (e * 8 < G.HX * G.esize[p]) ((double *)(stages + (size_t)s * G.stage_bytes + G.off[p]))[e] = 0.0;
+            if (e * 8 < HX * G.esize[p]) ((double *)(stages + (size_t)s * LY::stage + G.off[p]))[e] = 0.0;
         }
     }
     __syncthreads();
@@ -166,138 +192,127 @@ k_cgp_a(const __grid_constant__ PipeGeom G, CgpState<R> S, R alpha_psi, R alpha_
     if (warp == CGP_WARPS) {
         cgp_produce<NS>(G, stages, full, empty, x0, ys - 1, ye);
     } else {
-        const R dx = (R)g.dx, dy = (R)g.dy, idx = (R)g.idx, idy = (R)g.idy, idx2 = (R)g.idx2, idy2 = (R)g.idy2;
+        const R dx = (R)g.dx, dy = (R)g.dy, idx = (R)g.idx, idy = (R)g.idy, idy2 = (R)g.idy2, idx2 = (R)g.idx2, idxy = (R)g.idxy;
         const int lc = warp * 31 + lane - 1;              // column inside the strip (-1: helper column of the first warp)
         const int col = x0 + lc;
-        const int c = lc + G.HX;                           // column inside the stage window
         const bool xin = col >= 0 && col < g.Nx;
         const bool outl = lane >= 1 && lc < G.WS && col < g.Nx;
-        // updated state of one row of this lane's column
+        // per-thread bases into stage 0: complex planes at tc, real planes at tr; a stage adds pos * LY::stage
+        const unsigned char *tc = stages + (size_t)(lc + HX) * sizeof(C), *tr = stages + (size_t)(lc + HX) * sizeof(R);
+        auto LC = [&](unsigned pos, int off, int dc) { return *(const C *)(tc + (pos & (NS - 1)) * LY::stage + off + dc * (int)sizeof(C)); };
+        auto LR = [&](unsigned pos, int off, int dc) { return *(const R *)(tr + (pos & (NS - 1)) * LY::stage + off + dc * (int)sizeof(R)); };
+        // column-dependent pieces of the b-edge stencil (boundary doubling of quirk Q10, cg.h:240-282)
+        const bool hasW = col > 0, hasE = col + 1 < g.Nx;
+        const R ddb = (col == 0 || col + 1 == g.Nx) ? (R)2 : (R)1;
+        const R rhb = col == 0 ? (R)2.0 * S.H * idx : (col + 1 == g.Nx ? (R)-2.0 * S.H * idx : (R)0);
+        const R dxdy = dx * dy, dxdy2 = (R)2.0 * dx * dy;
+        // running element offset of (col, y) in the pitched planes
+        size_t n = g.at(xin ? col : 0, ys - 1);
+        const bool mag = S.kappa2 > (R)0;
+
         struct Row { C p; R a, b, aW; unsigned f; R eps; };
-        auto stage_of = [&](int it) { return stages + (size_t)(it % NS) * G.stage_bytes; };
-        auto build = [&](const unsigned char *st, int r) {
+        auto build = [&](unsigned pos, size_t nn) {       // the (updated) state of this lane's node in the row at `pos`
             Row w;
-            w.p = ((const C *)(st + G.off[P_PSI]))[c];
+            w.p = LC(pos, LY::o_psi, 0);
             if (UPDATE) {
-                const C d = ((const C *)(st + G.off[P_D]))[c];
+                const C d = LC(pos, LY::o_d, 0);
                 w.p.x = alpha_psi * d.x + w.p.x; w.p.y = alpha_psi * d.y + w.p.y;        // axpy_c (utils.h:74-82)
             }
             w.a = 0; w.b = 0; w.aW = 0;
             if (HAVEA) {
-                w.a = ((const R *)(st + G.off[P_A]))[c]; w.b = ((const R *)(st + G.off[P_B]))[c];
-                w.aW = ((const R *)(st + G.off[P_A]))[c - 1];
+                w.a = LR(pos, LY::o_a, 0); w.b = LR(pos, LY::o_b, 0); w.aW = LR(pos, LY::o_a, -1);
                 if (SOLVEA && UPDATE) {
-                    w.a = alpha_A * ((const R *)(st + G.off[P_DA]))[c] + w.a;
-                    w.b = alpha_A * ((const R *)(st + G.off[P_DB]))[c] + w.b;
-                    w.aW = alpha_A * ((const R *)(st + G.off[P_DA]))[c - 1] + w.aW;
+                    w.a = alpha_A * LR(pos, LY::o_da, 0) + w.a;
+                    w.b = alpha_A * LR(pos, LY::o_db, 0) + w.b;
+                    w.aW = alpha_A * LR(pos, LY::o_da, -1) + w.aW;
                 }
             }
             w.f = 0; w.eps = S.eps;
             if (xin) {
-                const size_t n = g.at(col, r);
-                w.f = S.nf[n];
-                if (S.epsf) w.eps = S.epsf[n];
+                w.f = S.nf[nn];
+                if (S.epsf) w.eps = S.epsf[nn];
             } else { w.p.x = 0; w.p.y = 0; w.a = 0; w.b = 0; }
-            if (col - 1 < 0) w.aW = 0;
+            if (!hasW) w.aW = 0;
             return w;
         };
         // ---- prologue: row ys-1 (S neighbour of the first row) and row ys
-        int it = 0;
         cgp_wait(&full[0], 0);
-        Row prv = build(stage_of(0), ys - 1);
-        R sbP = 0, cbP = 1, bEP = 0;
-        if (prv.f & (NF_MP | NF_PP)) sincos_r<R>(dy * prv.b, &sbP, &cbP);
+        Row prv = build(0u, n);
+        R sbP, cbP, bEP = 0;
+        {
+            R t0, t1;
+            cgp_sincos2<R>((R)0, dy * prv.b, t0, t1, sbP, cbP);
+        }
         if (HAVEA) {
-            const unsigned char *st = stage_of(0);
-            bEP = ((const R *)(st + G.off[P_B]))[c + 1];
-            if (SOLVEA && UPDATE) bEP = alpha_A * ((const R *)(st + G.off[P_DB]))[c + 1] + bEP;
+            bEP = LR(0u, LY::o_b, 1);
+            if (SOLVEA && UPDATE) bEP = alpha_A * LR(0u, LY::o_db, 1) + bEP;
         }
         __syncwarp();
         if (lane == 0) cgp_arrive(&empty[0]);
-        it = 1;
-        cgp_wait(&full[1 % NS], (uint32_t)((1 / NS) & 1));
-        Row cur = build(stage_of(1), ys);
-        for (int y = ys; y < ye; y++, it++) {
-            // `it` = ring position of row y; row y+1 sits at it+1
-            const int itn = it + 1;
-            cgp_wait(&full[itn % NS], (uint32_t)((itn / NS) & 1));
-            const Row nxt = build(stage_of(itn), y + 1);
-            const unsigned char *st = stage_of(it);
+        n += g.P;
+        cgp_wait(&full[1 & (NS - 1)], (1 / NS) & 1);
+        Row cur = build(1u, n);
+        unsigned pos = 1;
+        for (int y = ys; y < ye; y++, pos++, n += g.P) {
+            // `pos` = ring position of row y; row y+1 sits at pos+1
+            cgp_wait(&full[(pos + 1) & (NS - 1)], ((pos + 1) / NS) & 1);
+            const Row nxt = build(pos + 1, n + g.P);
             // E / W neighbours of row y (updated on the fly from the raw stage values)
-            C pE = ((const C *)(st + G.off[P_PSI]))[c + 1], pW = ((const C *)(st + G.off[P_PSI]))[c - 1];
+            C pE = LC(pos, LY::o_psi, 1), pW = LC(pos, LY::o_psi, -1);
             if (UPDATE) {
-                const C dE = ((const C *)(st + G.off[P_D]))[c + 1], dW = ((const C *)(st + G.off[P_D]))[c - 1];
+                const C dE = LC(pos, LY::o_d, 1), dW = LC(pos, LY::o_d, -1);
                 pE.x = alpha_psi * dE.x + pE.x; pE.y = alpha_psi * dE.y + pE.y;
                 pW.x = alpha_psi * dW.x + pW.x; pW.y = alpha_psi * dW.y + pW.y;
             }
             R bE = 0, bW = 0;
             if (HAVEA) {
-                bE = ((const R *)(st + G.off[P_B]))[c + 1]; bW = ((const R *)(st + G.off[P_B]))[c - 1];
+                bE = LR(pos, LY::o_b, 1); bW = LR(pos, LY::o_b, -1);
                 if (SOLVEA && UPDATE) {
-                    bE = alpha_A * ((const R *)(st + G.off[P_DB]))[c + 1] + bE;
-                    bW = alpha_A * ((const R *)(st + G.off[P_DB]))[c - 1] + bW;
+                    bE = alpha_A * LR(pos, LY::o_db, 1) + bE;
+                    bW = alpha_A * LR(pos, LY::o_db, -1) + bW;
                 }
             }
             // previous gradient of this node (PR sums)
             C q; q.x = 0; q.y = 0;
             R qa = 0, qb = 0;
             if (GRAD && PREV) {
-                q = ((const C *)(st + G.off[P_GP]))[c];
-                if (SOLVEA) { qa = ((const R *)(st + G.off[P_GP + 1]))[c]; qb = ((const R *)(st + G.off[P_GP + 2]))[c]; }
+                q = LC(pos, LY::o_g, 0);
+                if (SOLVEA) { qa = LR(pos, LY::o_ga, 0); qb = LR(pos, LY::o_gb, 0); }
             }
-            // link variables of this node's E and N links; the W link is the neighbouring lane's E link
-            const unsigned f = cur.f;
-            R sa = 0, ca = 1, sb = 0, cb = 1;
-            if (f & (NF_PM | NF_PP)) sincos_r<R>(dx * cur.a, &sa, &ca);
-            if (f & (NF_MP | NF_PP)) sincos_r<R>(dy * cur.b, &sb, &cb);
+            // link variables of this node's E and N links (evaluated whether or not the link carries weight: the weight
+            // table zeroes what must not count); the W link is the neighbouring lane's E link
+            R sa, ca, sb, cb;
+            cgp_sincos2<R>(dx * cur.a, dy * cur.b, sa, ca, sb, cb);
             const R sW = __shfl_up_sync(CGP_FULL, sa, 1), cW = __shfl_up_sync(CGP_FULL, ca, 1);
             if (outl) {
-                const size_t n = g.at(col, y);
+                const R *wt = lut + cur.f * W_N;
                 const C p0 = cur.p;
-                const R eps = cur.eps;
-                C gj; gj.x = 0; gj.y = 0;
-                R e = 0;
-                if (f) {
-                    R wW, wE, wS, wN, gw;
-                    cgp_du_w<R>(f, wW, wE, wS, wN, gw);
-                    const R p2 = p0.x * p0.x + p0.y * p0.y;
-                    if (UPDATE) e += gw * ((R)0.5 * p2 - eps) * p2;
-                    const R p = p2 - eps;
-                    gj.x += (R)2.0 * gw * p * p0.x;
-                    gj.y += (R)2.0 * gw * p * p0.y;
-                    // g_grad_jac_psi(psi0, ph, psi1) = 2 (psi0 - psi1 U(ph))  (cg.h:5-12); W and S links enter with
-                    // the opposite phase: sincos(-x) = (-sin x, cos x)
-                    if (f & (NF_MM | NF_MP)) {
-                        const C z = cgp_gradc<R, C>(p0, -sW, cW, pW);
-                        gj.x += wW * idx2 * ((R)-2.0 * z.x); gj.y += wW * idx2 * ((R)-2.0 * z.y);
-                    }
-                    if (f & (NF_PM | NF_PP)) {
-                        const C z = cgp_gradc<R, C>(p0, sa, ca, pE);
-                        gj.x += wE * idx2 * ((R)-2.0 * z.x); gj.y += wE * idx2 * ((R)-2.0 * z.y);
-                        if (UPDATE) e += wE * idx2 * (z.x * z.x + z.y * z.y);
-                    }
-                    if (f & (NF_MM | NF_PM)) {
-                        const C z = cgp_gradc<R, C>(p0, -sbP, cbP, prv.p);
-                        gj.x += wS * idy2 * ((R)-2.0 * z.x); gj.y += wS * idy2 * ((R)-2.0 * z.y);
-                    }
-                    if (f & (NF_MP | NF_PP)) {
-                        const C z = cgp_gradc<R, C>(p0, sb, cb, nxt.p);
-                        gj.x += wN * idy2 * ((R)-2.0 * z.x); gj.y += wN * idy2 * ((R)-2.0 * z.y);
-                        if (UPDATE) e += wN * idy2 * (z.x * z.x + z.y * z.y);
-                    }
-                }
-                if (UPDATE && S.kappa2 > (R)0 && col < g.Nx - 1 && y < g.Ny - 1) {
-                    R dB = -S.H;
-                    if (HAVEA) dB += idx * (bE - cur.b) - idy * (nxt.a - cur.a);
-                    e += S.kappa2 * dB * dB;
-                }
+                const R p2 = p0.x * p0.x + p0.y * p0.y;
+                // g_grad_jac_psi(psi0, ph, psi1) = 2 (psi0 - psi1 U(ph))  (cg.h:5-12); W and S links enter with the
+                // opposite phase: sincos(-x) = (-sin x, cos x)
+                const C zW = cgp_gradc<R, C>(p0, -sW, cW, pW), zE = cgp_gradc<R, C>(p0, sa, ca, pE);
+                const C zS = cgp_gradc<R, C>(p0, -sbP, cbP, prv.p), zN = cgp_gradc<R, C>(p0, sb, cb, nxt.p);
                 if (UPDATE) {
+                    R e = wt[W_G] * ((R)0.5 * p2 - cur.eps) * p2;
+                    e += wt[W_EE] * (zE.x * zE.x + zE.y * zE.y);
+                    e += wt[W_EN] * (zN.x * zN.x + zN.y * zN.y);
+                    if (mag && col < g.Nx - 1 && y < g.Ny - 1) {
+                        R dB = -S.H;
+                        if (HAVEA) dB += idx * (bE - cur.b) - idy * (nxt.a - cur.a);
+                        e += S.kappa2 * dB * dB;
+                    }
                     acc[0] += (double)e;
                     psi_out[n] = p0;
                     if (SOLVEA) { a_out[n] = cur.a; b_out[n] = cur.b; }
                 }
                 if (GRAD) {
-                    const R dxdy = dx * dy;
+                    const R pl = wt[W_G2] * (p2 - cur.eps);
+                    C gj;
+                    gj.x = pl * p0.x; gj.y = pl * p0.y;
+                    gj.x += wt[W_CW] * zW.x; gj.y += wt[W_CW] * zW.y;
+                    gj.x += wt[W_CE] * zE.x; gj.y += wt[W_CE] * zE.y;
+                    gj.x += wt[W_CS] * zS.x; gj.y += wt[W_CS] * zS.y;
+                    gj.x += wt[W_CN] * zN.x; gj.y += wt[W_CN] * zN.y;
                     gj.x *= dxdy; gj.y *= dxdy;
                     gpsi[n] = gj;
                     if (PREV) {
@@ -305,24 +320,29 @@ k_cgp_a(const __grid_constant__ PipeGeom G, CgpState<R> S, R alpha_psi, R alpha_
                         acc[2] += (double)(q.x * q.x + q.y * q.y);
                     }
                     if (SOLVEA) {
-                        const R pm = (f & NF_PM) ? (R)1 : (R)0, pp = (f & NF_PP) ? (R)1 : (R)0, mp = (f & NF_MP) ? (R)1 : (R)0;
-                        if (col < g.Nx - 1) {
-                            R w = S.kappa2 * cgp_curl_a<R>(g, y, S.H, cur.a, prv.a, nxt.a, prv.b, bEP, cur.b, bE);
-                            if (f & (NF_PM | NF_PP)) {
-                                const R js = (p0.x * pE.y - p0.y * pE.x) * ca - (p0.x * pE.x + p0.y * pE.y) * sa;
-                                w += -((R)0.5 * (pm + pp)) * idx * js;
-                            }
-                            w = (R)2.0 * dx * dy * w;
+                        if (col < g.Nx - 1) {      // dG/da on the a-edge (col, y): curl-curl with quirk Q10 (cg.h:176-217)
+                            const bool lo = y == 0, hi = y + 1 == g.Ny;
+                            const R dd = (lo || hi) ? (R)2 : (R)1;
+                            R v = lo ? (R)-2.0 * S.H * idy : (hi ? (R)2.0 * S.H * idy : (R)0);
+                            v += (R)2.0 * idy2 * cur.a;
+                            v += lo ? (R)0 : dd * (-idy2 * prv.a + idxy * prv.b - idxy * bEP);
+                            v += hi ? (R)0 : dd * (-idy2 * nxt.a - idxy * cur.b + idxy * bE);
+                            const R js = (p0.x * pE.y - p0.y * pE.x) * ca - (p0.x * pE.x + p0.y * pE.y) * sa;
+                            R w = S.kappa2 * v;
+                            w += wt[W_JE] * js;
+                            w = dxdy2 * w;
                             ga[n] = w;
                             if (PREV) { acc[3] += (double)(w * (w - qa)); acc[4] += (double)(qa * qa); }
                         }
-                        if (y < g.Ny - 1) {
-                            R w = S.kappa2 * cgp_curl_b<R>(g, col, S.H, cur.b, bW, bE, cur.aW, nxt.aW, cur.a, nxt.a);
-                            if (f & (NF_MP | NF_PP)) {
-                                const R js = (p0.x * nxt.p.y - p0.y * nxt.p.x) * cb - (p0.x * nxt.p.x + p0.y * nxt.p.y) * sb;
-                                w += -((R)0.5 * (mp + pp)) * idy * js;
-                            }
-                            w = (R)2.0 * dx * dy * w;
+                        if (y < g.Ny - 1) {        // dG/db on the b-edge (col, y) (cg.h:240-282)
+                            R v = rhb;
+                            v += (R)2.0 * idx2 * cur.b;
+                            v += hasW ? ddb * (-idx2 * bW + idxy * cur.aW - idxy * nxt.aW) : (R)0;
+                            v += hasE ? ddb * (-idx2 * bE - idxy * cur.a + idxy * nxt.a) : (R)0;
+                            const R js = (p0.x * nxt.p.y - p0.y * nxt.p.x) * cb - (p0.x * nxt.p.x + p0.y * nxt.p.y) * sb;
+                            R w = S.kappa2 * v;
+                            w += wt[W_JN] * js;
+                            w = dxdy2 * w;
                             gb[n] = w;
                             if (PREV) { acc[3] += (double)(w * (w - qb)); acc[4] += (double)(qb * qb); }
                         }
@@ -330,27 +350,30 @@ k_cgp_a(const __grid_constant__ PipeGeom G, CgpState<R> S, R alpha_psi, R alpha_
                 }
             }
             __syncwarp();
-            if (lane == 0) cgp_arrive(&empty[it % NS]);      // row y's stage is free
+            if (lane == 0) cgp_arrive(&empty[pos & (NS - 1)]);      // row y's stage is free
             prv = cur; sbP = sb; cbP = cb; bEP = bE;
             cur = nxt;
         }
         __syncwarp();
-        if (lane == 0) cgp_arrive(&empty[it % NS]);
+        if (lane == 0) cgp_arrive(&empty[pos & (NS - 1)]);
     }
     block_sum_to_partials<5>(acc, partials, blockIdx.x);
 }
 
 // ============================================================================================ pass B
-// planes: 0 psi, 1 g_psi, 2 d_psi(old), [3 a, 4 b], [5 ga, 6 gb, 7 da, 8 db]
 // NV = 5: c0..c4 (cg.h:400-467); NV = 17: c00..c04, c10..c14, c20..c24, c30, c40 (cg.h:528-701).
 // Quirk Q11: the coefficient kernels use the scalar eps only.
 template <typename R, int NV, bool HAVEA, int NS>
-__global__ void __launch_bounds__(CGP_THREADS, (NV == 17 && sizeof(R) == 8) ? 1 : 2)
+__global__ void __launch_bounds__(CGP_THREADS, 2)
 k_cgp_b(const __grid_constant__ PipeGeom G, CgpState<R> S, const double *__restrict__ beta,
         typename V2<R>::type *__restrict__ dpsi_new, R *__restrict__ da_new, R *__restrict__ db_new, double *partials) {
     typedef typename V2<R>::type C;
     constexpr bool SOLVEA = NV == 17;
+    typedef LayoutB<R, HAVEA, SOLVEA> LY;
+    constexpr int HX = LY::D::HX;
+    static_assert((NS & (NS - 1)) == 0, "NS must be a power of two");
     extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ R lut[16 * W_N];
     uint64_t *full = (uint64_t *)smem, *empty = full + NS;
     unsigned char *stages = smem + 128;
     const Geo &g = G.g;
@@ -358,16 +381,9 @@ k_cgp_b(const __grid_constant__ PipeGeom G, CgpState<R> S, const double *__restr
     const int cs = blockIdx.x % G.nstrips, rc = blockIdx.x / G.nstrips;
     const int x0 = cs * G.WS;
     const int ys = G.ylo + rc * G.L, ye = ys + G.L < G.yhi ? ys + G.L : G.yhi;
-    constexpr int P_PSI = 0, P_G = 1, P_D = 2, P_A = 3, P_B = 4, P_GA = 5, P_GB = 6, P_DA = 7, P_DB = 8;
 
-    if (tid == 0) {
-        for (int s = 0; s < NS; s++) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cgp_u32(&full[s])));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cgp_u32(&empty[s])), "r"(CGP_WARPS));
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
+    cgp_init_barriers(full, empty, NS);
+    cgp_fill_lut<R>(lut, g);
     __syncthreads();
 
     double v[NV];
@@ -376,113 +392,105 @@ k_cgp_b(const __grid_constant__ PipeGeom G, CgpState<R> S, const double *__restr
     if (warp == CGP_WARPS) {
         cgp_produce<NS>(G, stages, full, empty, x0, ys, ye);
     } else {
-        const R dx = (R)g.dx, dy = (R)g.dy, idx = (R)g.idx, idy = (R)g.idy, idx2 = (R)g.idx2, idy2 = (R)g.idy2;
-        // w is 0, 1/2 or 1, so (-w*i2)/3 == -w*(i2/3) bit for bit: the divisions of cg.h:600-640 leave the node loop
-        const R idx2_3 = idx2 / (R)3.0, idy2_3 = idy2 / (R)3.0, idx2_12 = idx2 / (R)12.0, idy2_12 = idy2 / (R)12.0;
+        const R dx = (R)g.dx, dy = (R)g.dy, idx = (R)g.idx, idy = (R)g.idy;
         const R beta_psi = (R)beta[0], beta_A = (R)beta[1];
         constexpr int C1 = NV == 17 ? 5 : 1, C2 = NV == 17 ? 10 : 2, C3 = NV == 17 ? 15 : 3, C4 = NV == 17 ? 16 : 4;
         const int lc = warp * 32 + lane;                  // no W neighbours here: warps do not overlap
         const int col = x0 + lc;
-        const int c = lc + G.HX;
         const bool xin = col < g.Nx;
         const bool outl = lc < G.WS && col < g.Nx;
+        const unsigned char *tc = stages + (size_t)(lc + HX) * sizeof(C), *tr = stages + (size_t)(lc + HX) * sizeof(R);
+        auto LC = [&](unsigned pos, int off, int dc) { return *(const C *)(tc + (pos & (NS - 1)) * LY::stage + off + dc * (int)sizeof(C)); };
+        auto LR = [&](unsigned pos, int off, int dc) { return *(const R *)(tr + (pos & (NS - 1)) * LY::stage + off + dc * (int)sizeof(R)); };
+        size_t n = g.at(xin ? col : 0, ys);
+        const bool mag = S.kappa2 > (R)0;
         struct Row { C p, d; R a, b, da, db; unsigned f; };
-        auto stage_of = [&](int it) { return stages + (size_t)(it % NS) * G.stage_bytes; };
-        auto build = [&](const unsigned char *st, int r) {
+        auto build = [&](unsigned pos, size_t nn) {
             Row w;
-            w.p = ((const C *)(st + G.off[P_PSI]))[c];
-            const C gg = ((const C *)(st + G.off[P_G]))[c], dd = ((const C *)(st + G.off[P_D]))[c];
+            w.p = LC(pos, LY::o_psi, 0);
+            const C gg = LC(pos, LY::o_g, 0), dd = LC(pos, LY::o_d, 0);
             w.d.x = beta_psi * dd.x - gg.x; w.d.y = beta_psi * dd.y - gg.y;                 // axmy_c (utils.h:97-104)
             w.a = 0; w.b = 0; w.da = 0; w.db = 0;
-            if (HAVEA) { w.a = ((const R *)(st + G.off[P_A]))[c]; w.b = ((const R *)(st + G.off[P_B]))[c]; }
+            if (HAVEA) { w.a = LR(pos, LY::o_a, 0); w.b = LR(pos, LY::o_b, 0); }
             if (SOLVEA) {
-                w.da = beta_A * ((const R *)(st + G.off[P_DA]))[c] - ((const R *)(st + G.off[P_GA]))[c];
-                w.db = beta_A * ((const R *)(st + G.off[P_DB]))[c] - ((const R *)(st + G.off[P_GB]))[c];
+                w.da = beta_A * LR(pos, LY::o_da, 0) - LR(pos, LY::o_ga, 0);
+                w.db = beta_A * LR(pos, LY::o_db, 0) - LR(pos, LY::o_gb, 0);
             }
             w.f = 0;
-            if (xin) w.f = S.nf[g.at(col, r)];
+            if (xin) w.f = S.nf[nn];
             else { w.p.x = 0; w.p.y = 0; w.d.x = 0; w.d.y = 0; w.a = 0; w.b = 0; w.da = 0; w.db = 0; }
             return w;
         };
-        int it = 0;
         cgp_wait(&full[0], 0);
-        Row cur = build(stage_of(0), ys);
-        for (int y = ys; y < ye; y++, it++) {
-            const int itn = it + 1;
-            cgp_wait(&full[itn % NS], (uint32_t)((itn / NS) & 1));
-            const Row nxt = build(stage_of(itn), y + 1);
-            const unsigned char *st = stage_of(it);
-            const C pE = ((const C *)(st + G.off[P_PSI]))[c + 1];
+        Row cur = build(0u, n);
+        unsigned pos = 0;
+        for (int y = ys; y < ye; y++, pos++, n += g.P) {
+            cgp_wait(&full[(pos + 1) & (NS - 1)], ((pos + 1) / NS) & 1);
+            const Row nxt = build(pos + 1, n + g.P);
+            const C pE = LC(pos, LY::o_psi, 1);
             C dE;
             {
-                const C gg = ((const C *)(st + G.off[P_G]))[c + 1], dd = ((const C *)(st + G.off[P_D]))[c + 1];
+                const C gg = LC(pos, LY::o_g, 1), dd = LC(pos, LY::o_d, 1);
                 dE.x = beta_psi * dd.x - gg.x; dE.y = beta_psi * dd.y - gg.y;
             }
             R bE = 0, dbE = 0;
-            if (HAVEA) bE = ((const R *)(st + G.off[P_B]))[c + 1];
-            if (SOLVEA) dbE = beta_A * ((const R *)(st + G.off[P_DB]))[c + 1] - ((const R *)(st + G.off[P_GB]))[c + 1];
+            if (HAVEA) bE = LR(pos, LY::o_b, 1);
+            if (SOLVEA) dbE = beta_A * LR(pos, LY::o_db, 1) - LR(pos, LY::o_gb, 1);
+            R sE, cE, sN, cN;
+            cgp_sincos2<R>(dx * cur.a, dy * cur.b, sE, cE, sN, cN);
             if (outl) {
-                const size_t n = g.at(col, y);
-                const unsigned f = cur.f;
-                if (f) {
-                    R wW, wE, wS, wN, gw;
-                    cgp_du_w<R>(f, wW, wE, wS, wN, gw);
-                    const C p0 = cur.p, d0 = cur.d;
-                    const R p2 = p0.x * p0.x + p0.y * p0.y, d2 = d0.x * d0.x + d0.y * d0.y;
-                    const R tw = (R)2.0 * (p0.x * d0.x + p0.y * d0.y);
-                    v[0] += (double)(gw * ((R)0.5 * p2 - S.eps) * p2);
-                    v[C1] += (double)(gw * tw * (p2 - S.eps));
-                    v[C2] += (double)(gw * (-S.eps * d2 + (R)0.5 * tw * tw + p2 * d2));
-                    v[C3] += (double)(gw * tw * d2);
-                    v[C4] += (double)(gw * (R)0.5 * d2 * d2);
+                const R *wt = lut + cur.f * W_N;
+                const C p0 = cur.p, d0 = cur.d;
+                const R gw = wt[W_G];
+                const R p2 = p0.x * p0.x + p0.y * p0.y, d2 = d0.x * d0.x + d0.y * d0.y;
+                const R tw = (R)2.0 * (p0.x * d0.x + p0.y * d0.y);
+                v[0] += (double)(gw * ((R)0.5 * p2 - S.eps) * p2);
+                v[C1] += (double)(gw * tw * (p2 - S.eps));
+                v[C2] += (double)(gw * (-S.eps * d2 + (R)0.5 * tw * tw + p2 * d2));
+                v[C3] += (double)(gw * tw * d2);
+                v[C4] += (double)(gw * (R)0.5 * d2 * d2);
 #pragma unroll
-                    for (int dir = 0; dir < 2; dir++) {
-                        const bool on = dir == 0 ? (f & (NF_PM | NF_PP)) : (f & (NF_MP | NF_PP));
-                        if (!on) continue;
-                        const R w = dir == 0 ? wE : wN, i2 = dir == 0 ? idx2 : idy2, d = dir == 0 ? dx : dy;
-                        const R i2_3 = dir == 0 ? idx2_3 : idy2_3, i2_12 = dir == 0 ? idx2_12 : idy2_12;
-                        R ph = 0;
-                        if (HAVEA) ph += d * (dir == 0 ? cur.a : cur.b);
-                        R s, cc;
-                        sincos_r<R>(ph, &s, &cc);
-                        const C p1 = dir == 0 ? pE : nxt.p, d1 = dir == 0 ? dE : nxt.d;
-                        const C zp = cgp_gradc<R, C>(p0, s, cc, p1), zd = cgp_gradc<R, C>(d0, s, cc, d1);
-                        v[0] += (double)(w * i2 * (zp.x * zp.x + zp.y * zp.y));
-                        v[C1] += (double)(w * i2 * (R)2.0 * (zp.x * zd.x + zp.y * zd.y));
-                        v[C2] += (double)(w * i2 * (zd.x * zd.x + zd.y * zd.y));
-                        if (NV == 17) {
-                            const R dph = d * (dir == 0 ? cur.da : cur.db);
-                            const R dph2 = dph * dph;
-                            // z = x0 * U(-ph) * conj(x1), U(-ph) = c + i s
+                for (int dir = 0; dir < 2; dir++) {
+                    const R wi2 = wt[dir == 0 ? W_EE : W_EN];                 // w * i2
+                    const R s = dir == 0 ? sE : sN, cc = dir == 0 ? cE : cN;
+                    const C p1 = dir == 0 ? pE : nxt.p, d1 = dir == 0 ? dE : nxt.d;
+                    const C zp = cgp_gradc<R, C>(p0, s, cc, p1), zd = cgp_gradc<R, C>(d0, s, cc, d1);
+                    v[0] += (double)(wi2 * (zp.x * zp.x + zp.y * zp.y));
+                    v[C1] += (double)(wi2 * (R)2.0 * (zp.x * zd.x + zp.y * zd.y));
+                    v[C2] += (double)(wi2 * (zd.x * zd.x + zd.y * zd.y));
+                    if (NV == 17) {
+                        const R w3 = wt[dir == 0 ? W_E3 : W_N3], w12 = wt[dir == 0 ? W_E12 : W_N12];    // -w*i2/3, -w*i2/12
+                        const R dph = (dir == 0 ? dx : dy) * (dir == 0 ? cur.da : cur.db);
+                        const R dph2 = dph * dph;
+                        // z = x0 * U(-ph) * conj(x1), U(-ph) = c + i s
 #define CGP_ZMUL(x0_, x1_, zr, zi)                                           \
     {                                                                        \
         R ur = x0_.x * cc - x0_.y * s, ui = x0_.x * s + x0_.y * cc;          \
         zr = ur * x1_.x + ui * x1_.y;                                        \
         zi = ui * x1_.x - ur * x1_.y;                                        \
     }
-                            R zr, zi, z2r, z2i;
-                            CGP_ZMUL(p0, p1, zr, zi);
-                            v[1] += (double)(w * i2 * (R)2.0 * zi * dph);
-                            v[2] += (double)(w * i2 * zr * dph2);
-                            v[3] += (double)(-w * i2_3 * zi * dph2 * dph);
-                            v[4] += (double)(-w * i2_12 * zr * dph2 * dph2);
-                            CGP_ZMUL(p0, d1, zr, zi);
-                            CGP_ZMUL(d0, p1, z2r, z2i);
-                            zr += z2r; zi += z2i;
-                            v[6] += (double)(w * i2 * (R)2.0 * zi * dph);
-                            v[7] += (double)(w * i2 * zr * dph2);
-                            v[8] += (double)(-w * i2_3 * zi * dph2 * dph);
-                            v[9] += (double)(-w * i2_12 * zr * dph2 * dph2);
-                            CGP_ZMUL(d0, d1, zr, zi);
-                            v[11] += (double)(w * i2 * (R)2.0 * zi * dph);
-                            v[12] += (double)(w * i2 * zr * dph2);
-                            v[13] += (double)(-w * i2_3 * zi * dph2 * dph);
-                            v[14] += (double)(-w * i2_12 * zr * dph2 * dph2);
+                        R zr, zi, z2r, z2i;
+                        CGP_ZMUL(p0, p1, zr, zi);
+                        v[1] += (double)(wi2 * (R)2.0 * zi * dph);
+                        v[2] += (double)(wi2 * zr * dph2);
+                        v[3] += (double)(w3 * zi * dph2 * dph);
+                        v[4] += (double)(w12 * zr * dph2 * dph2);
+                        CGP_ZMUL(p0, d1, zr, zi);
+                        CGP_ZMUL(d0, p1, z2r, z2i);
+                        zr += z2r; zi += z2i;
+                        v[6] += (double)(wi2 * (R)2.0 * zi * dph);
+                        v[7] += (double)(wi2 * zr * dph2);
+                        v[8] += (double)(w3 * zi * dph2 * dph);
+                        v[9] += (double)(w12 * zr * dph2 * dph2);
+                        CGP_ZMUL(d0, d1, zr, zi);
+                        v[11] += (double)(wi2 * (R)2.0 * zi * dph);
+                        v[12] += (double)(wi2 * zr * dph2);
+                        v[13] += (double)(w3 * zi * dph2 * dph);
+                        v[14] += (double)(w12 * zr * dph2 * dph2);
 #undef CGP_ZMUL
-                        }
                     }
                 }
-                if (S.kappa2 > (R)0 && col < g.Nx - 1 && y < g.Ny - 1) {
+                if (mag && col < g.Nx - 1 && y < g.Ny - 1) {
                     if (NV == 17) {
                         R BH = -S.H;
                         if (HAVEA) BH += idx * (bE - cur.b) - idy * (nxt.a - cur.a);
@@ -499,11 +507,11 @@ k_cgp_b(const __grid_constant__ PipeGeom G, CgpState<R> S, const double *__restr
                 if (SOLVEA) { da_new[n] = cur.da; db_new[n] = cur.db; }
             }
             __syncwarp();
-            if (lane == 0) cgp_arrive(&empty[it % NS]);
+            if (lane == 0) cgp_arrive(&empty[pos & (NS - 1)]);
             cur = nxt;
         }
         __syncwarp();
-        if (lane == 0) cgp_arrive(&empty[it % NS]);
+        if (lane == 0) cgp_arrive(&empty[pos & (NS - 1)]);
     }
     block_sum_to_partials<NV>(v, partials, blockIdx.x);
 }
@@ -518,7 +526,7 @@ __global__ void k_cgp_beta(const double *__restrict__ sums, double *beta) {
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-template <typename R> static constexpr int cgp_ns() { return sizeof(R) == 8 ? 4 : 6; }
+template <typename R> static constexpr int cgp_ns() { return 4; }
 
 // strips of <= lout*8 output columns (multiple of 4: 16-byte aligned row windows in every plane), row chunks of L rows
 static void cgp_geom(svl_ctx *c, PipeGeom &G, int rsize, int lout, int L) {
@@ -588,6 +596,7 @@ static int cgp_pass_a_t(svl_ctx *c, int solveA, int do_update, int do_grad, int 
     do {                                                                                                            \
         auto kern = k_cgp_a<R, HA, SA, UP, GR, PV, NS>;                                                             \
         SVL_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+        SVL_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
         kern<<<nb, CGP_THREADS, smem, c->stream>>>(G, S, (R)alpha_psi, (R)alpha_A, po, ao, bo, gp, gA0, gA1, c->partials); \
     } while (0)
     const int key = (havea ? 16 : 0) | (solveA ? 8 : 0) | (do_update ? 4 : 0) | (do_grad ? 2 : 0) | ((do_grad && have_prev) ? 1 : 0);
@@ -669,6 +678,7 @@ static int cgp_pass_b_t(svl_ctx *c, int solveA, double kappa2, double eps, doubl
     do {                                                                                                            \
         auto kern = k_cgp_b<R, NVV, HA, NS>;                                                                        \
         SVL_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+        SVL_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
         kern<<<nb, CGP_THREADS, smem, c->stream>>>(G, S, dbeta, dpo, dao, dbo, c->partials);                        \
     } while (0)
     if (solveA) CGP_B_LAUNCH(17, true);

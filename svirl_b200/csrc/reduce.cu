@@ -15,11 +15,11 @@ int svl_ensure_partials(svl_ctx *c, size_t n) {
     return 0;
 }
 
-// out[k] = scale * sum_b partials[b*nv + k]
+// out[k] = scale * sum_b partials[b*nv + k]; one CTA per component (fixed order inside a CTA: reproducible)
 __global__ void __launch_bounds__(256) k_final_sum(const double *__restrict__ partials, int nblocks, int nv,
                                                    double scale, double *__restrict__ out) {
     __shared__ double sm[8];
-    for (int k = 0; k < nv; k++) {
+    for (int k = blockIdx.x; k < nv; k += gridDim.x) {
         double s = 0.0;
         for (int b = threadIdx.x; b < nblocks; b += 256) s += partials[(size_t)b * nv + k];
         s = warp_sum(s);
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) k_final_sum(const double *__restrict__ pa
 
 int svl_finish_sum(svl_ctx *c, int nblocks, int nv, double scale, double *out_host) {
     SVL_REQUIRE(nv <= 64, "too many reduction components");
-    k_final_sum<<<1, 256, 0, c->stream>>>(c->partials, nblocks, nv, scale, c->d_result);
+    k_final_sum<<<nv, 256, 0, c->stream>>>(c->partials, nblocks, nv, scale, c->d_result);
     SVL_CHECK(cudaGetLastError());
     c->stat_launches += 1;
     if (out_host) {

@@ -23,6 +23,22 @@ def _h(x):
     return x.handle if hasattr(x, 'handle') else None
 
 
+def _horner2d(x, y, rows):
+    """numpy.polynomial.polynomial.polyval2d(x, y, c) for Python floats x, y and c given as nested lists: Horner in x
+    down the rows (a vector over the columns, starting from c[-1] + x*0 like polyval), then Horner in y; the same
+    IEEE operations in the same order, hence the same bits."""
+    n, m = len(rows), len(rows[0])
+    z = x * 0.0
+    r = [v + z for v in rows[n - 1]]
+    for i in range(n - 2, -1, -1):
+        ci = rows[i]
+        r = [ci[k] + r[k] * x for k in range(m)]
+    v = r[m - 1] + y * 0.0
+    for k in range(m - 2, -1, -1):
+        v = r[k] + v * y
+    return v
+
+
 class CG(object):
 
     def __init__(self, par, mesh, _vars, params, observables):
@@ -107,6 +123,29 @@ class CG(object):
         return np.min(am)
 
     def _cg_alpha_min(self, alpha0=[0.0, 0.0], tol=1e-8):
+        """The reference's call: scipy.optimize.minimize(BFGS, tol=1e-8) on polyval2d(alpha, c) with the polyder
+        gradients (cg.py:378-419).  The objective and its gradient are evaluated by `_horner2d`, which performs
+        polyval2d's floating-point operations in polyval2d's order on Python floats: every value SciPy sees is
+        bit-identical (tests/test_linesearch_host.py compares x, nit and nfev with the verbatim numpy callables),
+        so the iterates are the reference's; it only skips numpy's per-call overhead (~0.4 ms per line search)."""
+        c = self.__c
+        P = np.polynomial.polynomial
+        C0, C1, CC = P.polyder(c, axis=0).tolist(), P.polyder(c, axis=1).tolist(), np.asarray(c, dtype=np.float64).tolist()
+        if np.asarray(c).dtype != np.float64:          # fp32 solver: keep numpy's own promotion rules
+            return self._cg_alpha_min_numpy(alpha0, tol)
+
+        def f(alpha):
+            return np.float64(_horner2d(float(alpha[0]), float(alpha[1]), CC))
+
+        def j(alpha):
+            x, y = float(alpha[0]), float(alpha[1])
+            return np.array([_horner2d(x, y, C0), _horner2d(x, y, C1)])
+
+        r = scipy.optimize.minimize(f, x0=np.array(alpha0), jac=j, method='BFGS', tol=tol)
+        return r.x
+
+    def _cg_alpha_min_numpy(self, alpha0=[0.0, 0.0], tol=1e-8):
+        """The same minimisation with numpy's polyval2d as the callables, exactly as written in cg.py:378-419."""
         c = self.__c
         P = np.polynomial.polynomial
         cj0 = P.polyder(c, axis=0)
@@ -121,6 +160,15 @@ class CG(object):
 
         r = scipy.optimize.minimize(f, x0=np.array(alpha0), jac=j, method='BFGS', tol=tol)
         return r.x
+
+    def _cg_alpha_min_native(self):
+        """Opt-in (cfg.cg_line_search = 'native'): the library's damped-Newton search on c / max|c|."""
+        c = self.__c
+        flat = (C.c_double * 17)(*([float(v) for v in c[0, :]] + [float(v) for v in c[1, :]] + [float(v) for v in c[2, :]]
+                                   + [float(c[3, 0]), float(c[4, 0])]))
+        out = (C.c_double * 2)()
+        _lib.call("svl_cg_line_search", flat, 1, out, None)
+        return np.array([out[0], out[1]])
 
     def _cg_alpha_min_scaled(self):
         """The same BFGS minimisation on c / max|c| (an O(1) objective)."""
@@ -147,8 +195,11 @@ class CG(object):
         reference call works are unaffected, so trajectory parity holds wherever the reference
         itself survives.  ``cfg.cg_line_search = 'normalized'`` (not a reference option) uses the
         normalised polynomial in every iteration."""
-        if getattr(cfg, 'cg_line_search', 'reference') == 'normalized':
+        mode = getattr(cfg, 'cg_line_search', 'reference')
+        if mode == 'normalized':
             return self._cg_alpha_min_scaled()
+        if mode == 'native':
+            return self._cg_alpha_min_native()
         c = self.__c
         P = np.polynomial.polynomial
         with np.errstate(all='ignore'):
