@@ -12,7 +12,14 @@ One JSON line on stdout (rank 0).  `value` = nodes * steps / device time with th
 in HBM; `e2e` = the same through the C ABI with HOST buffers (pinned psi up, one step, psi down,
 every step); `roofline` = algorithmic bytes of the psi sweep kernel / its launch time vs the
 measured HBM copy peak; `cpu_baseline` = the reference's own kernel source compiled for the host
-cores (oracle/_ref, kind "reference") or the NumPy port, on a bounded sample.
+cores (oracle/_ref, kind "reference") or the NumPy port, on a bounded sample.  Beside the contract keys:
+
+  parity        GPU psi after the cpu_baseline leg's steps vs the reference-kernel psi of that leg (same seeded state)
+  gpu_baseline  "B-ref": the UNMODIFIED reference package with its own CUDA kernels on this GPU (baseline/bref.py)
+  also          the other BASELINE configs on this GPU: cfg3 (8192^2 fp64 kappa=2 TDGL), cfg4s (8192^2 fp64 CG
+                iterations, the second half of BASELINE's metric), cfg1 (README 129^2), each with its roofline and B-ref
+  strong        BASELINE configs[4]: 32768^2 fp64 kappa=inf split over the N GPUs of this run (strong scaling)
+  slab_bitwise  N > 1: a 300 x 401 run on the N slabs equals the single-GPU run bit for bit (checked before timing)
 
 --impl reference times that CPU arm alone (the reference has no CPU path and pyCUDA cannot be
 installed offline).  With --gpus N > 1 (launched under torchrun, one rank per GPU)
@@ -256,31 +263,100 @@ def cpu_reference_steps(wl, nsteps, warmup=0):
             if 1.0e-4 * float(r2[0]) < 1.0:
                 break
     el = time.perf_counter() - t0
-    return N * nsteps / el, dict(kind="reference", cores=os.cpu_count(), sweeps=sweeps, seconds=el, band=band)
+    return N * nsteps / el, dict(kind="reference", cores=os.cpu_count(), sweeps=sweeps, seconds=el, band=band,
+                                 psi=cur if (warmup == 0 and band is None) else None)
+
+
+# ------------------------------------------------------------------------------------ helpers
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f).get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback 6650 (B200_PROFILING.md)"
+
+
+def ncu_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json names
+    the kernel instantiation and the command each number was captured on); None when there is no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
+
+
+def solver_kwargs(wl):
+    kw = dict(Nx=wl["Nx"], Ny=wl["Ny"], dx=0.5, dy=0.5, dtype=wl["dtype"], gl_parameter=wl["kappa"],
+              normal_conductivity=wl["sigma"], homogeneous_external_field=wl["H"], random_seed=1234)
+    if wl["tiling"]:
+        kw["material_tiling"] = hole_tiling(wl["Nx"], wl["Ny"])
+    if wl["eps_field"]:
+        kw["linear_coefficient"] = (0.7 + 0.3 * np.random.RandomState(4321).rand(wl["Nx"], wl["Ny"])).astype(wl["dtype"])
+    return kw
+
+
+def bref_td(wl, steps, warmup=3):
+    """B-ref: the reference's own solver + kernels on this GPU, same seeded workload (TDGL steps)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import bref
+    if not bref.available():
+        return {"unavailable": "baseline/_ref not installed (baseline/install_ref.py)"}
+    gl = bref.make_solver(**solver_kwargs(wl))
+    el, sp, sa = bref.time_td(gl, steps, warmup)
+    N = wl["Nx"] * wl["Ny"]
+    out = {"kind": "reference-kernels-sm100", "value": N * steps / el, "unit": UNIT, "ms_per_step": 1e3 * el / steps,
+           "steps": steps, "warmup": warmup, "sweeps_psi": int(sp), "sweeps_A": int(sa),
+           "how": "unmodified reference package (baseline/_ref) on baseline/gpu_pycuda: block 128, one thread per node, per "
+                  "sweep fill + launch + blocking 4-byte read-back (svirl/solvers/td.py:164-202, 274-311); wall clock"}
+    del gl
+    return out
+
+
+def bref_cg(wl, iters, td_steps=20):
+    """B-ref CG iterations (svirl/solvers/cg.py:477-544 as written, SciPy line search) after `td_steps` TDGL steps."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import bref
+    if not bref.available():
+        return {"unavailable": "baseline/_ref not installed (baseline/install_ref.py)"}
+    gl = bref.make_solver(**solver_kwargs(wl))
+    gl.solve.td(dt=0.1, Nt=td_steps)
+    with np.errstate(all="ignore"):
+        el, E = bref.time_cg(gl, iters, warmup=0)
+    fin = int(np.sum(np.isfinite(np.array(E, dtype=np.float64))))
+    out = {"kind": "reference-kernels-sm100", "value": iters / el, "unit": "iterations/s", "ms_per_iter": 1e3 * el / iters,
+           "iterations": iters, "energies": E, "finite_iterations": fin,
+           "how": "unmodified reference package on baseline/gpu_pycuda; the first `iterations` CG iterations after the TDGL "
+                  "steps (no warm-up: its SciPy BFGS line search runs away after 3 iterations at this size, "
+                  "profiles/r02_cfg4_adjudicate_8192.json)"}
+    del gl
+    return out
 
 
 # ------------------------------------------------------------------------------------ CG mode
-def bench_cg(args, wl, gl, par, N):
-    """Hot path 2: modified nonlinear-CG iterations (metric: CG iterations / s), single GPU.
-    20 TDGL steps leave the random initial state, W warm-up iterations, then K timed ones; the
-    host line search (numpy polyroots / SciPy BFGS, the reference's calls) is inside the timed
-    region because it is part of an iteration."""
+def measure_cg(wl, gl, par, steps, warmup, line_search=None, td_steps=20):
+    """Hot path 2: K timed CG iterations through gl.solve.cg() (metric: CG iterations / s) after `td_steps` TDGL steps
+    (skipped when td_steps = 0) and W warm-up iterations.  The host line search is inside the timed region because it
+    is part of an iteration.  line_search: None / "reference" = SciPy BFGS / polyroots exactly as the reference calls
+    them (redone on the normalised polynomial only when BFGS runs away; rescues are counted), "native" = the
+    library's own search (opt-in)."""
     from svirl_b200 import _lib
-    gl.solve.td(dt=0.1, Nt=20)
-    if args.line_search:
-        gl.cfg.cg_line_search = args.line_search        # default "reference": SciPy BFGS as in the reference, redone on the
-                                                        # normalised polynomial only when it runs away (rescues are counted)
+    N = wl["Nx"] * wl["Ny"]
+    if td_steps:
+        gl.solve.td(dt=0.1, Nt=td_steps)
+    gl.cfg.cg_line_search = line_search or "reference"
     gl.cfg.convergence_rtol = 0.0
     gl.solve._init_cg()
     gl.solve._cg._CG__convergence_rtol = -1.0          # never stop early: time exactly K iterations
-    gl.solve.cg(n_iter=max(args.warmup, 3))
+    gl.solve._cg.line_search_rescues = 0
+    gl.solve.cg(n_iter=max(warmup, 3))
     par.synchronize()
     l0 = par.stat("launches")
     sampler = ClockSampler(0)
     sampler.start()
     t0 = time.perf_counter()
     _lib.call("svl_event_record", par.ctx, 0)
-    gl.solve.cg(n_iter=args.steps)
+    gl.solve.cg(n_iter=steps)
     _lib.call("svl_event_record", par.ctx, 1)
     ms = C.c_double()
     _lib.call("svl_event_elapsed_ms", par.ctx, 0, 1, C.byref(ms))
@@ -291,71 +367,156 @@ def bench_cg(args, wl, gl, par, N):
     R = np.dtype(wl["dtype"]).itemsize
     finite = not np.isinf(wl["kappa"])
     per_iter = (36 * R + 2) if finite else (22 * R + 2)          # fused lower bounds
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = per_iter * N * args.steps / (ms.value * 1e-3) / 1e9
+    peak, peak_src = hbm_peak()
+    achieved = per_iter * N * steps / (ms.value * 1e-3) / 1e9
     E = gl.solve._cg.cg_energies
-    cpu = None
-    if not args.no_cpu_baseline:
-        # NumPy port of the same iteration on a bounded sample: a 768^2 sub-problem with the same
-        # parameters (the cost per node does not depend on the grid size), scaled to this grid
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import glnumpy as O
-        ns = 768
-        og = O.Grid(ns, ns, 0.5, 0.5, wl["dtype"])
-        op = O.initial_psi(og, 1.0, 1234)
-        oa, ob = O.initial_A(og, wl["H"])
-        omt = hole_tiling(ns, ns) if wl["tiling"] else None
-        op, oa, ob, _ = O.td_run(og, 0.1, 3, 1.0, omt, wl["kappa"], wl["sigma"], wl["H"], op, oa, ob, rand_t=1234)
-        tc = time.perf_counter()
-        nit = 3
-        O.cg_run(og, nit, wl["kappa"], 1.0, wl["H"], omt, op, np.zeros_like(oa), np.zeros_like(ob), oa, ob, rtol=-1.0)
-        tc = time.perf_counter() - tc
-        cpu = {"value": nit / tc * (ns * ns) / N, "unit": "iterations/s", "cores": 1, "kind": "port",
-               "sample": "%d NumPy-oracle CG iterations on a 768^2 grid with the same parameters (%.1f s), "
-                         "scaled by the node ratio to %dx%d" % (nit, tc, wl["Nx"], wl["Ny"])}
-    line = {"metric": "cg_iters_per_s", "value": args.steps / (ms.value * 1e-3), "unit": "iterations/s", "n_gpus": 1,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms.value / args.steps,
+    return {"metric": "cg_iters_per_s", "value": steps / (ms.value * 1e-3), "unit": "iterations/s", "n_gpus": 1,
+            "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms.value / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if wl["dtype"] is np.float32 else "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "Nx": wl["Nx"], "Ny": wl["Ny"], "seed": 1234,
-                       "line_search": gl.cfg.cg_line_search},
+                       "line_search": gl.cfg.cg_line_search, "l2": "working set exceeds the 126 MB L2"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "bytes_per_node_iter": per_iter,
-                         "note": "algorithmic bytes = fused lower bound of SURVEY 8d; includes the host line search time"},
-            "cpu_baseline": cpu, "clocks": clocks, "gpu_launches": int(launches),
-            "wall_ms_per_iter": 1e3 * wall / args.steps, "energy_first_last": [float(E[0]), float(E[-1])], "energies": [float(e) for e in E],
+                         "traffic": ncu_traffic("cg_pass_a_%s" % wl.get("key", "")), "bytes_per_node_iter": per_iter,
+                         "peak_source": peak_src, "kernel": "k_cgp_a + k_cgp_b (two passes per iteration)",
+                         "note": "algorithmic bytes = fused lower bound of SURVEY 8d (36R+2 finite kappa, 22R+2 kappa=inf); "
+                                 "the iteration time includes the host line search"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "wall_ms_per_iter": 1e3 * wall / steps, "energy_first_last": [float(E[0]), float(E[-1])],
+            "energies": [float(e) for e in E],
             "energy_decreasing": bool(np.all(np.diff(np.array(E, dtype=np.float64)) < 0)),
             "line_search_rescues": int(gl.solve._cg.line_search_rescues),
-            "e2e": {"value": args.steps / wall, "unit": "iterations/s", "h2d_bytes_per_step": 0,
+            "e2e": {"value": steps / wall, "unit": "iterations/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 8 * (17 if finite else 5) + 8,
                     "api": "gl.solve.cg(): per iteration the 5/17 coefficients and the energy come back to the host"}}
+
+
+def cg_cpu_baseline(wl):
+    """NumPy port of the same iteration on a bounded sample: a 768^2 sub-problem with the same parameters (the cost
+    per node does not depend on the grid size), scaled to this grid."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import glnumpy as O
+    N = wl["Nx"] * wl["Ny"]
+    ns = 768
+    og = O.Grid(ns, ns, 0.5, 0.5, wl["dtype"])
+    op = O.initial_psi(og, 1.0, 1234)
+    oa, ob = O.initial_A(og, wl["H"])
+    omt = hole_tiling(ns, ns) if wl["tiling"] else None
+    op, oa, ob, _ = O.td_run(og, 0.1, 3, 1.0, omt, wl["kappa"], wl["sigma"], wl["H"], op, oa, ob, rand_t=1234)
+    tc = time.perf_counter()
+    nit = 3
+    O.cg_run(og, nit, wl["kappa"], 1.0, wl["H"], omt, op, np.zeros_like(oa), np.zeros_like(ob), oa, ob, rtol=-1.0)
+    tc = time.perf_counter() - tc
+    return {"value": nit / tc * (ns * ns) / N, "unit": "iterations/s", "cores": 1, "kind": "port",
+            "sample": "%d NumPy-oracle CG iterations on a 768^2 grid with the same parameters (%.1f s), "
+                      "scaled by the node ratio to %dx%d" % (nit, tc, wl["Nx"], wl["Ny"])}
+
+
+def bench_cg(args, wl, gl, par, N):
+    line = measure_cg(wl, gl, par, args.steps, args.warmup, args.line_search)
+    line["cpu_baseline"] = None if args.no_cpu_baseline else cg_cpu_baseline(wl)
     print(json.dumps(line))
 
 
+def measure_td(wl, gl, par, steps, warmup):
+    """K timed TDGL steps on one GPU (device time on the library's stream) -> the contract keys of a line."""
+    from svirl_b200 import _lib
+    N = wl["Nx"] * wl["Ny"]
+    gl.solve.td(dt=0.1, Nt=max(warmup, 3))
+    td = gl.solve._td
+    par.synchronize()
+    s0 = (td.sweeps_order_parameter, td.sweeps_vector_potential)
+    l0 = par.stat("launches")
+    sampler = ClockSampler(0)
+    sampler.start()
+    _lib.call("svl_event_record", par.ctx, 0)
+    gl.solve.td(dt=0.1, Nt=steps)
+    _lib.call("svl_event_record", par.ctx, 1)
+    ms = C.c_double()
+    _lib.call("svl_event_elapsed_ms", par.ctx, 0, 1, C.byref(ms))
+    par.synchronize()
+    clocks = sampler.stop()
+    sw_psi, sw_A = td.sweeps_order_parameter - s0[0], td.sweeps_vector_potential - s0[1]
+    bpsi, bA = bytes_per_node_sweep(wl)
+    peak, peak_src = hbm_peak()
+    achieved = (sw_psi * bpsi + sw_A * bA) * N / (ms.value * 1e-3) / 1e9
+    return {"metric": METRIC, "value": N * steps / (ms.value * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps,
+            "warmup": max(warmup, 3), "ms_per_step": ms.value / steps,
+            "dtype": "f32" if wl["dtype"] is np.float32 else "f64",
+            "config": {"workload": wl["name"], "Nx": wl["Nx"], "Ny": wl["Ny"], "dt": 0.1, "seed": 1234},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "bytes_per_node_sweep": [bpsi, bA], "sweeps_psi": int(sw_psi),
+                         "sweeps_A": int(sw_A), "traffic": None},
+            "clocks": clocks, "gpu_launches": int(par.stat("launches") - l0), "replays": par.stat("replays")}
+
+
+def also_blocks(args):
+    """The other BASELINE configs on this GPU (N = 1 only), each beside the reference's own kernels (B-ref).  A failure in
+    one block is recorded in that block and does not touch the main line."""
+    out = {}
+
+    def guarded(name, fn):
+        t0 = time.perf_counter()
+        try:
+            out[name] = fn()
+        except Exception as e:                       # noqa: BLE001 -- the main line must survive
+            out[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        out[name]["seconds"] = time.perf_counter() - t0
+
+    def cfg3():
+        wl = workload("cfg3")
+        gl = make_solver(wl)
+        r = measure_td(wl, gl, gl.par, 5, 3)
+        gl.par.close()
+        del gl
+        r["gpu_baseline"] = bref_td(wl, 3, 2)
+        return r
+
+    def cfg4s():
+        wl = dict(workload("cfg4s"), key="cfg4s")
+        gl = make_solver(wl)
+        r = measure_cg(wl, gl, gl.par, 10, 3, "reference")
+        nat = measure_cg(wl, gl, gl.par, 10, 3, "native", td_steps=0)
+        r["native_line_search"] = {k: nat[k] for k in ("value", "ms_per_step", "wall_ms_per_iter", "energy_decreasing")}
+        r["native_line_search"]["roofline_frac"] = nat["roofline"]["frac"]
+        r["native_line_search"]["note"] = ("cfg.cg_line_search = 'native' (opt-in, SURVEY row f3): the library's trust-region "
+                                           "Newton search instead of SciPy BFGS; same minimiser to ~1e-8")
+        gl.par.close()
+        del gl
+        r["gpu_baseline"] = bref_cg(wl, 3)
+        return r
+
+    def cfg1():
+        wl = workload("cfg1")
+        gl = make_solver(wl)
+        r = measure_td(wl, gl, gl.par, 200, 50)
+        gl.par.close()
+        del gl
+        r["gpu_baseline"] = bref_td(wl, 200, 50)
+        return r
+
+    for name, fn in (("cfg3", cfg3), ("cfg4s", cfg4s), ("cfg1", cfg1)):
+        if name in args.also.split(","):
+            guarded(name, fn)
+    return out
+
+
 # ------------------------------------------------------------------------------------ scale mode (cfg5)
-def bench_scale(args, wl, rank, world, local):
+def measure_scale(wl, rank, world, local, steps, warmup, opts=()):
     """BASELINE configs[4]: grids whose fields do not fit full-size host arrays, through
-    svirl_b200.scale.ScaleTD (slab-local seeded fields, row slabs over NVLink, GPU vortex count)."""
+    svirl_b200.scale.ScaleTD (slab-local seeded fields, row slabs over NVLink, GPU vortex count).  Needs the default
+    process group when world > 1.  -> the line (dict) on rank 0, None elsewhere."""
     import torch
     import torch.distributed as dist
     from svirl_b200 import _lib
     from svirl_b200.scale import ScaleTD
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
     Nx, Ny = wl["Nx"], wl["Ny"] * (world if wl["scale"] == "weak" else 1)
     N = Nx * Ny
     t_build = time.perf_counter()
     st = ScaleTD(Nx, Ny, 0.5, 0.5, wl["dtype"], wl["kappa"], wl["sigma"], wl["H"], 1.0, 1234, 1.0, device_id=local,
                  distributed=world > 1)
     t_build = time.perf_counter() - t_build
-    for kv in args.opt:
+    for kv in opts:
         k, v = kv.split("=")
         _lib.call("svl_set_option", st._ctx, k.encode(), int(v))
 
@@ -365,7 +526,7 @@ def bench_scale(args, wl, rank, world, local):
             dist.barrier()
         torch.cuda.synchronize()
 
-    st.td(0.1, max(args.warmup, 3))
+    st.td(0.1, max(warmup, 3))
     barrier()
     s0 = (st.sweeps[0], st.sweeps[1])
     l0 = st.stat("launches")
@@ -373,7 +534,7 @@ def bench_scale(args, wl, rank, world, local):
     sampler.start()
     t0 = time.perf_counter()
     _lib.call("svl_event_record", st._ctx, 0)
-    st.td(0.1, args.steps)
+    st.td(0.1, steps)
     _lib.call("svl_event_record", st._ctx, 1)
     ms = C.c_double()
     _lib.call("svl_event_elapsed_ms", st._ctx, 0, 1, C.byref(ms))
@@ -390,33 +551,39 @@ def bench_scale(args, wl, rank, world, local):
     else:
         t_ms = ms.value
     npos, nneg = int(t[2].item()), int(t[3].item())
+    line = None
     if rank == 0:
         sw_psi, sw_A = st.sweeps[0] - s0[0], st.sweeps[1] - s0[1]
         bpsi, bA = bytes_per_node_sweep(wl)
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak, peak_src = hbm_peak()
         achieved = (sw_psi * bpsi + sw_A * bA) * (N // world) / (t_ms * 1e-3) / 1e9
-        line = {"metric": METRIC, "value": N * args.steps / (t_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "higher_is_better": True,
+        line = {"metric": METRIC, "value": N * steps / (t_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+                "warmup": max(warmup, 3), "ms_per_step": t_ms / steps, "higher_is_better": True,
                 "scaling": wl["scale"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": wl["name"], "Nx": Nx, "Ny": Ny, "dt": 0.1, "seed": 1234,
                            "l2": "working set exceeds the 126 MB L2", "rows_per_gpu": Ny // world},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "kernel": "psi Jacobi sweep", "bytes_per_node_sweep": bpsi,
-                             "sweeps_psi": int(sw_psi), "sweeps_A": int(sw_A)},
+                             "sweeps_psi": int(sw_psi), "sweeps_A": int(sw_A), "peak_source": peak_src},
                 "cpu_baseline": None, "clocks": clocks, "gpu_launches": int(st.stat("launches") - l0),
                 "vortices": {"positive": npos, "negative": nneg, "how": "GPU winding pass, reference thresholds"},
                 "build_s": t_build,
-                "e2e": {"value": N * args.steps / wall, "unit": UNIT, "h2d_bytes_per_step": 0,
-                        "d2h_bytes_per_step": int(16 * (npos + nneg) / max(args.steps, 1)),
+                "e2e": {"value": N * steps / wall, "unit": UNIT, "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": int(16 * (npos + nneg) / max(steps, 1)),
                         "api": "ScaleTD.td(dt, Nt) + ScaleTD.vortex_count(): fields stay on the GPUs, the vortex list comes back"}}
-        print(json.dumps(line))
     st.close()
+    return line
+
+
+def bench_scale(args, wl, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    line = measure_scale(wl, rank, world, local, args.steps, args.warmup, args.opt)
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -435,6 +602,8 @@ def main():
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (svl_set_option)")
     ap.add_argument("--ny-mult", type=int, default=1, help="multiply Ny (to run an N-GPU weak-scaling grid on fewer GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--also", default="cfg3,cfg4s,cfg1", help="extra single-GPU configs reported in `also` (default line only)")
+    ap.add_argument("--no-extras", action="store_true", help="main line only: no parity / gpu_baseline / also / strong blocks")
     ap.add_argument("--line-search", default=None, choices=[None, "reference", "normalized", "native"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -479,6 +648,17 @@ def main():
     torch.cuda.set_device(local)
 
     from svirl_b200 import _lib
+    extras = (not args.no_extras) and args.workload == "cfg2" and args.ny_mult == 1
+    slab_bitwise = None
+    if world > 1 and extras:
+        # correctness of what is about to be timed: a 300 x 401 grid on these N slabs equals the single-GPU run bit for bit
+        # (psi-only fp32 and finite-kappa fp64, with holes; tests/slab_gpu_check.py)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import slab_gpu_check
+        try:
+            slab_bitwise = bool(slab_gpu_check.check(local, verbose=False))
+        except Exception as e:                   # noqa: BLE001
+            slab_bitwise = "error: %s" % (str(e)[:200],)
     gl = make_solver(wl, device_id=local, slab="auto" if world > 1 else None)
     par = gl.par
     if args.psi_kernel is not None:
@@ -551,6 +731,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_val = N * e2e_steps / e2e_s
+    replays = par.stat("replays")
+
+    # ---- BASELINE configs[4] on the same N GPUs: 32768^2 fp64 kappa=inf, STRONG scaling (all ranks take part)
+    strong = None
+    if extras:
+        del pin_in, pin_out, h_in, h_out
+        gl.par.close()
+        del gl
+        try:
+            strong = measure_scale(workload("cfg5"), rank, world, local, 10, 3)
+        except Exception as e:                   # noqa: BLE001 -- the main line must survive
+            strong = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
     if rank != 0:
         if world > 1:
@@ -558,34 +750,54 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (psi Jacobi sweep)
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak, peak_src = hbm_peak()
     bpsi, bA = bytes_per_node_sweep(wl)
     alg_bytes = (sw_psi * bpsi + sw_A * bA) * (N // world)      # per GPU: the roofline is a per-device quantity
     achieved = alg_bytes / (t_ms * 1e-3) / 1e9
-    # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this command
-    # (profiles/r01_ncu_psi_tile_f32_k4_cfg2.txt: dram__bytes_read.sum + dram__bytes_write.sum)
-    traffic = 122.6e6 if (args.workload == "cfg2" and world == 1 and args.psi_kernel in (None, 2)
-                          and args.psi_k in (None, 4)) else None
+    # DRAM bytes per launch of the dominant kernel: read from the committed ncu capture that names the kernel
+    # instantiation and command it was taken on (profiles/ncu_traffic.json); None when this run is not that command
+    tr = ncu_traffic("cfg2_psi_tile") if (args.workload == "cfg2" and world == 1 and args.psi_kernel in (None, 2)
+                                          and args.psi_k in (None, 4)) else None
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "traffic_note": "bytes per 4-sweep launch (ncu); algorithmic bytes of the same launch: "
-                                                "%d" % (4 * bpsi * (N // world)), "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650",
+            "traffic": tr["dram_bytes_per_launch"] if tr else None,
+            "traffic_note": ("%s; algorithmic bytes of the same launch: %d" % (tr["what"], 4 * bpsi * (N // world))) if tr else None,
+            "peak_source": peak_src,
             "kernel": "psi Jacobi sweep", "bytes_per_node_sweep": bpsi, "sweeps_psi": int(sw_psi),
             "sweeps_A": int(sw_A), "launches": int(launches),
             "avg_launch_us": 1e3 * t_ms / max(launches, 1)}
 
-    cpu = None
+    cpu, parity = None, None
     if not args.no_cpu_baseline and world == 1:
         nst = 25 if N <= 2048 * 2048 else 2            # ~10 s of host work at cfg2
         v, info = cpu_reference_steps(wl, nst, 0)
         cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                "sample": "%d full-grid TDGL steps from the seeded initial state (%d Jacobi sweeps, %.1f s)"
                          % (nst, info["sweeps"], info["seconds"])}
+        if info.get("psi") is not None:
+            # parity at the benchmark's own size: the same `nst` steps from the same seeded state on the GPU
+            # (a fresh solver) against the psi the reference kernel just produced on the host
+            try:
+                g2 = make_solver(wl, device_id=local)
+                g2.solve.td(Nt=nst, **td_kw)
+                got = g2.flatten_array(g2.vars.order_parameter)
+                ref = info["psi"]
+                err = float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-300))
+                tol = 1e-4 if wl["dtype"] is np.float32 else 1e-10
+                parity = {"max_rel": err, "tol": tol, "ok": bool(err < tol), "steps": nst, "sweeps_ref": int(info["sweeps"]),
+                          "sweeps_gpu": int(g2.solve._td.sweeps_order_parameter),
+                          "against": "reference kernel source on the host cores (oracle/_ref), psi after %d steps" % nst}
+                g2.par.close()
+                del g2
+            except Exception as e:               # noqa: BLE001
+                parity = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+    gpu_baseline, also = None, None
+    if extras and world == 1:
+        try:
+            gpu_baseline = bref_td(wl, max(3, min(args.steps, 20)), 3)
+        except Exception as e:                   # noqa: BLE001
+            gpu_baseline = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        also = also_blocks(args)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -594,8 +806,9 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(N * np.dtype(cdt).itemsize),
                     "d2h_bytes_per_step": int(N * np.dtype(cdt).itemsize), "steps": e2e_steps,
                     "api": "svl_h2d_rows + svl_td_run(1 step) + svl_d2h_rows on pinned host buffers"},
-            "gpu_launches": int(launches), "replays": par.stat("replays"),
-            "psi_kernel": int(args.psi_kernel) if args.psi_kernel is not None else None}
+            "gpu_launches": int(launches), "replays": replays,
+            "psi_kernel": int(args.psi_kernel) if args.psi_kernel is not None else None,
+            "parity": parity, "gpu_baseline": gpu_baseline, "slab_bitwise": slab_bitwise, "also": also, "strong": strong}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

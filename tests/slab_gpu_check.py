@@ -28,11 +28,9 @@ def run(kw, Nt, slab):
     return out
 
 
-def main():
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+def check(local, verbose=True):
+    """Runs inside an initialised NCCL process group; -> True on every rank iff all ranks agree bit for bit."""
+    rank = dist.get_rank()
     Nx, Ny = 300, int(os.environ.get("SLAB_NY", "401"))      # SLAB_NY=201 on 4 ranks: 50-row slabs (edge case)
     rs = np.random.RandomState(3)
     mt = rs.rand(Nx - 1, Ny - 1) > 0.1
@@ -50,15 +48,25 @@ def main():
         b_s, b_1 = ab_s[Na:].reshape(Ny - 1, Nx), ab_1[Na:].reshape(Ny - 1, Nx)
         same_a = np.array_equal(a_s[j0:j1], a_1[j0:j1]) and np.array_equal(b_s[j0:min(j1, Ny - 1)], b_1[j0:min(j1, Ny - 1)])
         good = same_psi and same_a and (ns, na) == (ns1, na1)
-        print("rank %d %s: rows [%d,%d) psi bitwise %s, A bitwise %s, sweeps %d/%d vs %d/%d -> %s"
-              % (rank, name, j0, j1, same_psi, same_a, ns, na, ns1, na1, "OK" if good else "MISMATCH"), flush=True)
+        if verbose:
+            print("rank %d %s: rows [%d,%d) psi bitwise %s, A bitwise %s, sweeps %d/%d vs %d/%d -> %s"
+                  % (rank, name, j0, j1, same_psi, same_a, ns, na, ns1, na1, "OK" if good else "MISMATCH"), flush=True)
         ok = ok and good
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return int(t.item()) == 1
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = check(local)
     dist.destroy_process_group()
     if rank == 0:
-        print("SLAB CHECK", "PASSED" if int(t.item()) == 1 else "FAILED", flush=True)
-    sys.exit(0 if int(t.item()) == 1 else 1)
+        print("SLAB CHECK", "PASSED" if ok else "FAILED", flush=True)
+    sys.exit(0 if ok else 1)
 
 
 if __name__ == "__main__":
