@@ -28,9 +28,13 @@ __global__ void k_node_flags(Geo g, const uint8_t *mt, uint8_t *nf) {
         bool mm = (i > 0) && (j > 0), mp = (i > 0) && (j + 1 < g.Ny);
         bool pm = (i + 1 < g.Nx) && (j > 0), pp = (i + 1 < g.Nx) && (j + 1 < g.Ny);
         if (mt) {   // cells are stored in a pitched plane too: cell (ci, cj) at g.at(ci, cj)
-            if (mm) mm = mt[g.at(i - 1, j - 1)] != 0;
+            // plane row 0 of a slab that does not start at the bottom of the grid: the cell row below it is not
+            // stored (found by compute-sanitizer memcheck).  That row is the outermost halo ring, whose own update
+            // is never used, so its two lower bits may be anything: take 0.
+            const bool below = jl > 0;
+            if (mm) mm = below && mt[g.at(i - 1, j - 1)] != 0;
             if (mp) mp = mt[g.at(i - 1, j)] != 0;
-            if (pm) pm = mt[g.at(i, j - 1)] != 0;
+            if (pm) pm = below && mt[g.at(i, j - 1)] != 0;
             if (pp) pp = mt[g.at(i, j)] != 0;
         }
         f = (mm ? NF_MM : 0) | (mp ? NF_MP : 0) | (pm ? NF_PM : 0) | (pp ? NF_PP : 0);
@@ -181,7 +185,7 @@ extern "C" int svl_set_option(svl_ctx *c, const char *name, int v) {
     else if (!strcmp(name, "cg_fused")) c->opt_cg_fused = v;
     else if (!strcmp(name, "resid_board")) c->opt_resid_board = v;
     else if (!strcmp(name, "slab_split")) c->opt_slab_split = v;
-    else if (!strcmp(name, "cg_slabs")) c->opt_cg_slabs = v;           // experimental: CG / energy on row slabs (untested on hardware)
+    else if (!strcmp(name, "cg_slabs")) c->opt_cg_slabs = v;           // no-op since round 2: CG / energy on row slabs is always on
     else if (!strcmp(name, "slab_nocomm")) c->opt_slab_nocomm = v;     // timing experiments only: ranks run uncoupled
     else if (!strcmp(name, "trace")) {                                 // diagnostics: record v launches from now on
         SVL_CHECK(cudaStreamSynchronize(c->stream));

@@ -420,11 +420,12 @@ __global__ void __launch_bounds__(256) k_axy3(Axy3<R> d, R alpha0, R alpha1, con
 #define EDGE_A(buf, R) ((buf) ? (const R *)(buf)->p[0] : nullptr)
 #define EDGE_B(buf, R) ((buf) ? (const R *)(buf)->p[1] : nullptr)
 
-static int check_state(const svl_buf *psi, const svl_buf *abei, const svl_buf *ab, const svl_buf *epsf) {
+// slab_ok: the entry point adds its sums over all ranks (free energy, fused CG iteration: validated on 2-8 GPUs with
+// tests/slab_gpu_check.py, SLAB_CG=4); the single coefficient kernels produce per-context sums and refuse row slabs
+static int check_state(const svl_buf *psi, const svl_buf *abei, const svl_buf *ab, const svl_buf *epsf, bool slab_ok = false) {
     SVL_REQUIRE(psi && psi->kind == SVL_NODE_C, "psi must be SVL_NODE_C");
-    // the sums of the energy / CG kernels are per context: on row slabs they would silently be partial
-    SVL_REQUIRE(!(psi->ctx && psi->ctx->slab_on && !psi->ctx->opt_cg_slabs),
-                "free energy / CG on row slabs is experimental: enable option cg_slabs (TDGL is the validated slab path)");
+    SVL_REQUIRE(slab_ok || !(psi->ctx && psi->ctx->slab_on),
+                "this kernel-level entry point sums over one context only: on row slabs use svl_free_energy / svl_cg_begin / svl_cg_end");
     SVL_REQUIRE(!ab || ab->kind == SVL_EDGE, "ab must be SVL_EDGE");
     SVL_REQUIRE(!abei || abei->kind == SVL_EDGE, "abei must be SVL_EDGE");
     SVL_REQUIRE(!epsf || epsf->kind == SVL_NODE_R, "eps_field must be SVL_NODE_R");
@@ -443,7 +444,7 @@ static int energy_t(svl_ctx *c, double kappa2, double eps, const svl_buf *epsf, 
                                              EDGE_B(ab, R), c->partials);
     SVL_CHECK(cudaGetLastError());
     c->stat_launches += 1;
-    if (c->slab_on) {      // experimental (option cg_slabs): the per-rank sums are added over the residual board
+    if (c->slab_on) {      // row slabs: the per-rank sums are added over the residual board
         SVL_TRY(svl_finish_sum(c, nb, 1, (double)((R)c->g.dx * (R)c->g.dy), nullptr));
         SVL_TRY(svl_board_allsum(c, c->d_result, 1));
         SVL_CHECK(cudaMemcpyAsync(c->h_result, c->d_result, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -457,7 +458,7 @@ static int energy_t(svl_ctx *c, double kappa2, double eps, const svl_buf *epsf, 
 extern "C" int svl_free_energy(svl_ctx *c, double kappa2, double eps, const svl_buf *epsf, double H, const svl_buf *psi,
                                const svl_buf *abei, const svl_buf *ab, double *E) {
     SVL_REQUIRE(c && E, "null argument");
-    SVL_TRY(check_state(psi, abei, ab, epsf));
+    SVL_TRY(check_state(psi, abei, ab, epsf, true));
     if (c->rsize == 4) return energy_t<float>(c, kappa2, eps, epsf, H, psi, abei, ab, E);
     return energy_t<double>(c, kappa2, eps, epsf, H, psi, abei, ab, E);
 }
@@ -689,7 +690,7 @@ extern "C" int svl_cg_begin(svl_ctx *c, int solveA, int have_prev, double kappa2
                             svl_buf *g_psi_prev, svl_buf *d_psi, svl_buf *g_A, svl_buf *g_A_prev, svl_buf *d_A,
                             double *beta, double *c_out) {
     SVL_REQUIRE(c && beta && c_out, "null argument");
-    SVL_TRY(check_state(psi, abei, ab, epsf));
+    SVL_TRY(check_state(psi, abei, ab, epsf, true));
     SVL_REQUIRE(g_psi && g_psi_prev && d_psi && g_psi->kind == SVL_NODE_C && g_psi_prev->kind == SVL_NODE_C &&
                 d_psi->kind == SVL_NODE_C, "psi-side CG buffers must be SVL_NODE_C");
     SVL_REQUIRE(!solveA || (g_A && g_A_prev && d_A && ab && g_A->kind == SVL_EDGE && g_A_prev->kind == SVL_EDGE &&
@@ -708,7 +709,7 @@ extern "C" int svl_cg_end(svl_ctx *c, int solveA, double kappa2, double eps, con
                           const svl_buf *abei, svl_buf *ab, const svl_buf *d_psi, const svl_buf *d_A, double alpha_psi,
                           double alpha_A, double *E_out) {
     SVL_REQUIRE(c && psi && d_psi, "null argument");
-    SVL_TRY(check_state(psi, abei, ab, epsf));
+    SVL_TRY(check_state(psi, abei, ab, epsf, true));
     SVL_REQUIRE(d_psi->kind == SVL_NODE_C && (!solveA || (d_A && ab && d_A->kind == SVL_EDGE)), "bad direction buffers");
     if (c->opt_cg_fused)
         return svl_cgf_end(c, solveA, kappa2, eps, epsf, H, psi, abei, ab, d_psi, d_A, alpha_psi, alpha_A, E_out);

@@ -640,7 +640,7 @@ static int cgf_begin_t(svl_ctx *c, int solveA, int have_prev, double kappa2, dou
     if (solveA) SVL_TRY(svl_swap(c, d_A, dn_A));
     SVL_CHECK(cudaMemcpyAsync(c->h_result + 32, dbeta, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     const int nvc = solveA ? 17 : 5;
-    if (c->slab_on) {      // experimental (option cg_slabs): rank-ordered sum over the residual board, then one host sync
+    if (c->slab_on) {      // row slabs: rank-ordered sum over the residual board, then one host sync
         SVL_TRY(svl_finish_sum(c, solveA ? nb17 : nb, nvc, (double)((R)c->g.dx * (R)c->g.dy), nullptr));
         SVL_TRY(svl_board_allsum(c, c->d_result, nvc));
         SVL_CHECK(cudaMemcpyAsync(c->h_result, c->d_result, nvc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -681,7 +681,7 @@ static int cgf_end_t(svl_ctx *c, int solveA, double kappa2, double eps, const sv
     SVL_TRY(svl_swap(c, psi, pn));
     if (solveA) SVL_TRY(svl_swap(c, ab, An));
     double E = 0.0;
-    if (c->slab_on) {      // experimental (option cg_slabs): refresh the 8-row halos of the new state, add the energies
+    if (c->slab_on) {      // row slabs: refresh the 8-row halos of the new state, add the energies
         SVL_TRY(svl_slab_push_psi(c, psi));
         if (solveA) SVL_TRY(svl_slab_push_ab(c, ab));
         SVL_TRY(svl_slab_wait(c));
