@@ -10,6 +10,9 @@ int svl_psi_stream_fit_k(int K);
 int svl_launch_psi_tile(svl_ctx *c, int K, double dt, double eps, const svl_buf *epsf, const svl_buf *ab,
                         const svl_buf *rhs, const svl_buf *psi, svl_buf *out, double lang_c, uint32_t rand_t,
                         unsigned long long *resid_slots);     // psi_tile.cu
+int svl_td_small_run(svl_ctx *c, int Nt, double dt, int solveA, double eps, const svl_buf *epsf, double kappa2, double rho,
+                     double H, svl_buf *psi, svl_buf *ab, double lang_psi, double lang_A, uint32_t *rand_t, double stop_psi,
+                     double stop_A, long long *sweeps, bool *handled);   // td_small.cu
 int svl_launch_a_tile(svl_ctx *c, int K, double dt, double kappa2, double rho, double H, const svl_buf *psi,
                       const svl_buf *rhs, const svl_buf *ab, svl_buf *out, double lang_c, uint32_t rand_t,
                       unsigned long long *resid_slots);       // a_tile.cu
@@ -532,6 +535,13 @@ extern "C" int svl_td_run(svl_ctx *c, int Nt, double dt, int solveA, double eps,
                           double rho, double H, svl_buf *psi, svl_buf *ab, double lang_psi, double lang_A,
                           uint32_t *rand_t, double stop_psi, double stop_A, long long *sweeps) {
     SVL_REQUIRE(c && rand_t, "null argument");
+    {   // small grids: the whole call in one launch of one thread-block cluster (option "graphs", td_small.cu)
+        SVL_TRY(check_kinds(psi, ab, epsf));
+        bool handled = false;
+        SVL_TRY(svl_td_small_run(c, Nt, dt, solveA, eps, epsf, kappa2, rho, H, psi, ab, lang_psi, lang_A, rand_t, stop_psi,
+                                 stop_A, sweeps, &handled));
+        if (handled) return 0;
+    }
     for (int t = 0; t < Nt; t++) {
         int n = 0;
         SVL_TRY(svl_td_psi_solve(c, dt, eps, epsf, ab, psi, lang_psi, *rand_t, stop_psi, &n));

@@ -33,11 +33,15 @@ def relerr(x, ref):
 KERNELS = [("plain", 0, 1, 1), ("stream_k4_tma", 1, 4, 1), ("stream_k1_tma", 1, 1, 1), ("stream_k3_tma", 1, 3, 1),
            ("stream_k6_tma", 1, 6, 1), ("stream_k4_ldg", 1, 4, 0),
            ("tile_k4", 2, 4, 1), ("tile_k1", 2, 1, 1), ("tile_k3", 2, 3, 1), ("tile_k8", 2, 8, 1),
-           ("tile_k4_plainA", 2, 4, 1, 0)]        # 5th entry: A-sweep kernel (0 per-node, default 1 = pair tile kernel)
+           ("tile_k4_plainA", 2, 4, 1, 0),        # 5th entry: A-sweep kernel (0 per-node, default 1 = pair tile kernel)
+           ("small", -1, 0, 0)]                   # the single-launch cluster kernel for small grids (td_small.cu)
 
 
 def set_kernel(gl, kernel):
     _, pk, k, tma = kernel[:4]
+    gl.par.set_option("graphs", 1 if pk < 0 else 0)      # the fixtures are small grids: choose the path explicitly
+    if pk < 0:
+        return
     gl.par.set_option("a_kernel", kernel[4] if len(kernel) > 4 else 1)
     gl.par.set_option("psi_kernel", pk)
     gl.par.set_option("psi_k", k)
@@ -181,8 +185,8 @@ def test_cg_full_first_iterations(name):
     assert np.all(np.diff(E) < 0)          # energy decreases monotonically
 
 
-@pytest.mark.parametrize("kernel", [KERNELS[0], KERNELS[1], KERNELS[6], KERNELS[10]],
-                         ids=["plain", "stream_k4_tma", "tile_k4", "tile_k4_plainA"])
+@pytest.mark.parametrize("kernel", [KERNELS[0], KERNELS[1], KERNELS[6], KERNELS[10], KERNELS[11]],
+                         ids=["plain", "stream_k4_tma", "tile_k4", "tile_k4_plainA", "small"])
 def test_cfg1_readme_1000_steps(kernel):
     """BASELINE configs[0]: 129^2, kappa 5, sigma 200, H 0.1, fp64, td(0.1, 1000): psi, a, b within
     1e-10, identical sweep counts, identical vortex count and positions."""
@@ -452,9 +456,10 @@ def test_td_fixed_vortices(name):
     assert np.abs(gl.vars._vp.get_d_obj().get() - d["vp_dev2"]).max() < tol * max(np.abs(d["vp_dev2"]).max(), 1.0)
 
 
-@pytest.mark.parametrize("shape", [(4, 4), (5, 9), (33, 31), (64, 65), (130, 7)], ids=lambda s: "%dx%d" % s)
+@pytest.mark.parametrize("graphs", [0, 1], ids=["batched", "small"])
+@pytest.mark.parametrize("shape", [(4, 4), (5, 9), (33, 31), (64, 65), (130, 7), (181, 181)], ids=lambda s: "%dx%d" % s)
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_small_and_ragged_grids_against_oracle(shape, dtype):
+def test_small_and_ragged_grids_against_oracle(shape, dtype, graphs):
     """Edge cases of the geometry: the minimum grid (4x4), sizes below / across one tile and one warp,
     odd pitches: TDGL (finite kappa, random holes, eps field) and a CG iteration against the NumPy oracle."""
     import glnumpy as O
@@ -465,6 +470,7 @@ def test_small_and_ragged_grids_against_oracle(shape, dtype):
     eps = (0.7 + 0.3 * rs.rand(Nx, Ny)).astype(dtype)
     gl = GLSolver(Nx=Nx, Ny=Ny, dx=0.5, dy=0.4, dtype=dtype, gl_parameter=2.0, normal_conductivity=10.0,
                   homogeneous_external_field=0.1, random_seed=3, material_tiling=mt, linear_coefficient=eps)
+    gl.par.set_option("graphs", graphs)
     g = O.Grid(Nx, Ny, 0.5, 0.4, dtype)
     psi0 = gl.vars.order_parameter
     a0, b0 = [x.copy() for x in gl.vars.vector_potential]

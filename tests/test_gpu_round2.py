@@ -56,7 +56,7 @@ def test_vortices_bitwise_on_reference_state(name, vector, monkeypatch):
 
 @pytest.mark.parametrize("shape", [(96, 80), (131, 71)], ids=["holes", "ragged"])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("kernel", [(0, 1), (2, 4), (2, 1), (1, 4)], ids=["plain", "tile_k4", "tile_k1", "stream_k4"])
+@pytest.mark.parametrize("kernel", [(0, 1), (2, 4), (2, 1), (1, 4), (-1, 0)], ids=["plain", "tile_k4", "tile_k1", "stream_k4", "small"])
 def test_jacobi_diagonal_vanishes_on_inactive_nodes(shape, dtype, kernel):
     """dt = 1.0 with linear coefficient 1.0: on inactive nodes D = 1 + dt*(0 - eps + 0) = 0.  The reference
     writes psi = 0 there (td.h:117); a branch-free 1/D must not seed NaNs."""
@@ -72,8 +72,10 @@ def test_jacobi_diagonal_vanishes_on_inactive_nodes(shape, dtype, kernel):
         mt = rs.rand(Nx - 1, Ny - 1) > 0.3
     gl = GLSolver(Nx=Nx, Ny=Ny, dx=1.0, dy=1.0, dtype=dtype, homogeneous_external_field=0.05, random_seed=3,
                   material_tiling=mt, linear_coefficient=1.0)
-    gl.par.set_option("psi_kernel", kernel[0])
-    gl.par.set_option("psi_k", kernel[1])
+    gl.par.set_option("graphs", 1 if kernel[0] < 0 else 0)
+    if kernel[0] >= 0:
+        gl.par.set_option("psi_kernel", kernel[0])
+        gl.par.set_option("psi_k", kernel[1])
     g = O.Grid(Nx, Ny, 1.0, 1.0, dtype)
     psi0 = gl.vars.order_parameter
     a0, b0 = [v.copy() for v in gl.vars.vector_potential]
