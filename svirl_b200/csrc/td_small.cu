@@ -3,11 +3,11 @@
 // At the README size (129^2, BASELINE configs[0]) a Jacobi sweep is a microsecond of work and the step time is launch
 // and synchronisation latency: the reference pays fill + launch + blocking read-back per sweep (svirl/solvers/td.py:164-202,
 // 274-311: ~1 ms per step), the batched drivers of td.cu two host round trips per step (0.105 ms).  Here a cluster of up
-// to 16 CTAs (hardware cluster barrier, ~0.3 us) keeps the whole solve on the device: every thread owns up to NPT nodes
-// with their constants in registers (right-hand side, the four link coefficients w*dt/d^2*exp(-+i d A) -- one sincos per
-// link and SOLVE --, 1/diagonal); per sweep it reads the four neighbours from L2 (ld.cg: the iterate is written by other
-// SMs), writes its nodes, the max-norm update goes through one atomicMax per CTA, and after the cluster barrier every
-// thread evaluates the reference's stop test (td.h:124-132 + td.py:198-201) on the same word.  psi-solve, A-solve (with the
+// to 16 CTAs (hardware cluster barrier) keeps the whole solve on the device: every thread owns up to NPT nodes with their
+// constants in registers (right-hand side, the four link coefficients w*dt/d^2*exp(-+i d A) -- one sincos per link and
+// SOLVE --, 1/diagonal); the iterate lives in shared memory (halo rows pushed to the neighbouring CTAs through
+// distributed shared memory), the per-CTA max-norm updates are broadcast the same way, and after the cluster barrier
+// every thread evaluates the reference's stop test (td.h:124-132 + td.py:198-201) on the same numbers.  psi-solve, A-solve (with the
 // link-phase aliasing quirk Q1), Langevin noise and the rand_t bookkeeping follow td.cu / the reference exactly; the
 // sweep counts are the reference's (tests: README fixture, 1000 steps).  The host synchronises once per td() call.
 // This is the "graphs" option of the library (north_star: launch overhead on small grids), default on; grids above
@@ -23,15 +23,15 @@ namespace cg = cooperative_groups;
 template <typename R> struct SmallArgs {
     Geo g;
     int Nt, solveA;
+    int M;                               // nodes per CTA (linear node index n = rank * M + m, x fastest); M >= Nx
     R dt, eps, kappa2, rho, H, lang_psi, lang_A;
     double stop_psi, stop_A;
     const R *epsf;
     const uint8_t *nf;
-    typename V2<R>::type *psi[3];        // [0] the caller's buffer (state), [1], [2] scratch
-    R *a[3], *b[3];
+    typename V2<R>::type *psi;           // state, updated in place
+    R *a, *b;
     uint32_t rand_t;
-    unsigned long long *ring;            // 4 residual words, zero on entry
-    long long *out;                      // psi sweeps, A sweeps, index of the buffer holding psi / A at the end, rand_t
+    long long *out;                      // psi sweeps, A sweeps, rand_t
 };
 
 __device__ __forceinline__ bool ts_stop(double r, double eps, bool fp32) {
@@ -40,51 +40,89 @@ __device__ __forceinline__ bool ts_stop(double r, double eps, bool fp32) {
     if (v > 1.0e8) v = 1.0e8;
     return (int)v < 10000;
 }
-template <typename T> __device__ __forceinline__ T ts_ld(const T *p) { return __ldcg(p); }
 
+// The iterate lives in SHARED memory: CTA `rank` owns the M consecutive nodes [rank*M, rank*M + M) and keeps them, plus a
+// halo of Nx nodes on either side (the rows above and below), in a double-buffered array; a sweep reads only local shared
+// memory, writes its nodes locally and -- for the first / last Nx nodes -- into the neighbouring CTA's halo through
+// distributed shared memory.  Global memory is touched at the start and at the end of a solve.
 template <typename R, int NPT>
 __global__ void __launch_bounds__(TS_THREADS, 1) k_td_small(const __grid_constant__ SmallArgs<R> A) {
     typedef typename V2<R>::type C;
     cg::cluster_group cl = cg::this_cluster();
     const Geo &g = A.g;
-    const int T = gridDim.x * TS_THREADS, gt = blockIdx.x * TS_THREADS + threadIdx.x;
-    const int P = g.P;
+    const int tid = threadIdx.x, rank = (int)cl.block_rank(), nct = (int)cl.num_blocks();
+    const int Nx = g.Nx, P = g.P, M = A.M, N = g.Nx * g.Ny, W = M + 2 * Nx;
     const bool fp32 = sizeof(R) == 4;
     const R dx = (R)g.dx, dy = (R)g.dy, idx = (R)g.idx, idy = (R)g.idy, idx2 = (R)g.idx2, idy2 = (R)g.idy2, idxy = (R)g.idxy;
     const R dt = A.dt, cx = dt * idx2, cy = dt * idy2;
+    extern __shared__ __align__(16) unsigned char ts_smem[];
+    C *X0 = (C *)ts_smem, *X1 = X0 + W;
+    unsigned long long *red = (unsigned long long *)(X1 + W);          // [2][TS_MAX_CTAS] per-CTA maxima of a sweep
+    // the neighbours' copies (halo pushes) and everybody's reduction slots
+    C *lo0 = rank > 0 ? cl.map_shared_rank(X0, rank - 1) : nullptr, *lo1 = rank > 0 ? cl.map_shared_rank(X1, rank - 1) : nullptr;
+    C *hi0 = rank + 1 < nct ? cl.map_shared_rank(X0, rank + 1) : nullptr, *hi1 = rank + 1 < nct ? cl.map_shared_rank(X1, rank + 1) : nullptr;
 
-    int off[NPT], ci[NPT], cj[NPT];
+    int off[NPT], ci[NPT], cj[NPT], L[NPT];
     unsigned fl[NPT];
     bool ok[NPT];
 #pragma unroll
     for (int k = 0; k < NPT; k++) {
-        const int nl = gt + k * T;
-        ok[k] = nl < g.Nx * g.Ny;
-        ci[k] = ok[k] ? nl % g.Nx : 0;
-        cj[k] = ok[k] ? nl / g.Nx : 0;
+        const int m = tid + k * TS_THREADS, n = rank * M + m;
+        ok[k] = m < M && n < N;
+        ci[k] = ok[k] ? n % Nx : 0;
+        cj[k] = ok[k] ? n / Nx : 0;
         off[k] = (cj[k] - g.rb) * P + ci[k];
+        L[k] = m + Nx;
         fl[k] = ok[k] ? A.nf[off[k]] : 0u;
     }
-    unsigned sidx = 0;                               // sweeps done by this launch: index into the residual ring
-    int pr[3] = {0, 1, 2}, ar[3] = {0, 1, 2};        // buffer roles: [0] state / iterate 0, [1], [2] ping-pong
+    unsigned sidx = 0;
     long long npsi = 0, nA = 0;
     uint32_t rand_t = A.rand_t;
 
-    // one sweep's epilogue: CTA max -> ring word, cluster barrier, everybody reads the same maximum
-    auto finish_sweep = [&](double rmax) {
-        block_max_to_slot(rmax, A.ring + (sidx & 3));
-        if (gt == 0) A.ring[(sidx + 2) & 3] = 0ull;  // free since everybody passed the previous barrier
+    // fill X0 (own nodes + both halos) from a global plane through `get`, clear X1; ends with a cluster barrier so that
+    // nobody pushes into a buffer that is still being initialised
+    auto load_state = [&](auto get) {
+        for (int q = tid; q < W; q += TS_THREADS) {
+            const int n = rank * M - Nx + q;
+            C v; v.x = 0; v.y = 0;
+            if (n >= 0 && n < N) v = get((n / Nx - g.rb) * P + n % Nx);
+            X0[q] = v;
+            C z; z.x = 0; z.y = 0;
+            X1[q] = z;
+        }
         cl.sync();
-        const unsigned long long bits = ts_ld(A.ring + (sidx & 3));
+    };
+    // store one node of the new iterate: locally and into the neighbour's halo
+    auto put = [&](C *out, C *olo, C *ohi, int k, C v) {
+        const int m = L[k] - Nx;
+        out[L[k]] = v;
+        if (olo && m < Nx) olo[M + Nx + m] = v;                 // my first Nx nodes = upper halo of rank-1
+        if (ohi && m >= M - Nx) ohi[m - (M - Nx)] = v;          // my last Nx nodes = lower halo of rank+1
+    };
+    // one sweep's epilogue: CTA max -> everybody's slot, cluster barrier, maximum over the CTAs
+    auto finish_sweep = [&](double rmax) {
+        __shared__ double sm_w[TS_THREADS / 32];
+        rmax = warp_max(rmax);
+        if ((tid & 31) == 0) sm_w[tid >> 5] = rmax;
+        __syncthreads();
+        unsigned long long *slot = red + (sidx & 1) * TS_MAX_CTAS;
+        if (tid < 32) {
+            double r = tid < TS_THREADS / 32 ? sm_w[tid] : 0.0;
+            r = warp_max(r);
+            r = __shfl_sync(0xffffffffu, r, 0);
+            if (tid < nct) cl.map_shared_rank(slot, tid)[rank] = (unsigned long long)__double_as_longlong(r);
+        }
+        cl.sync();
+        double r = 0.0;
+        for (int q = 0; q < nct; q++) r = fmax(r, __longlong_as_double((long long)slot[q]));
         sidx++;
-        return __longlong_as_double((long long)bits);
+        return r;
     };
 
     for (int step = 0; step < A.Nt; step++) {
         // ============================ psi solve (td.h:5-133; drivers td.py:157-218)
         {
-            C *B0 = A.psi[pr[0]], *S1 = A.psi[pr[1]], *S2 = A.psi[pr[2]];
-            const R *pa = A.a[ar[0]], *pb = A.b[ar[0]];
+            load_state([&](int o) { return __ldcg(A.psi + o); });
             C q[NPT], own[NPT], LW[NPT], LE[NPT], LS[NPT], LN[NPT];
             R di[NPT];
             const bool noise = A.lang_psi > (R)1.0e-32;
@@ -95,20 +133,20 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_td_small(const __grid_constan
                 if (!ok[k]) continue;
                 const int n = off[k];
                 const unsigned f = fl[k];
-                own[k] = ts_ld(B0 + n);
+                own[k] = X0[L[k]];
                 if (!f) continue;
                 C qq = own[k];
                 if (noise) {
-                    const uint32_t nn = (uint32_t)ci[k] + (uint32_t)g.Nx * (uint32_t)cj[k];
+                    const uint32_t nn = (uint32_t)ci[k] + (uint32_t)Nx * (uint32_t)cj[k];
                     qq.x += A.lang_psi * (rand_1<R>(nn, rand_t) - (R)0.5);
                     qq.y += A.lang_psi * (rand_2<R>(nn, rand_t) - (R)0.5);
                 }
                 const bool wW = f & (NF_MM | NF_MP), wE = f & (NF_PM | NF_PP), wS = f & (NF_MM | NF_PM), wN = f & (NF_MP | NF_PP);
                 R sn, cs;
-                if (wW) { sincos_r<R>(dx * ts_ld(pa + n - 1), &sn, &cs); LW[k].x = cx * cs; LW[k].y = cx * sn; }
-                if (wE) { sincos_r<R>(dx * ts_ld(pa + n), &sn, &cs); LE[k].x = cx * cs; LE[k].y = cx * sn; }
-                if (wS) { sincos_r<R>(dy * ts_ld(pb + n - P), &sn, &cs); LS[k].x = cy * cs; LS[k].y = cy * sn; }
-                if (wN) { sincos_r<R>(dy * ts_ld(pb + n), &sn, &cs); LN[k].x = cy * cs; LN[k].y = cy * sn; }
+                if (wW) { sincos_r<R>(dx * __ldcg(A.a + n - 1), &sn, &cs); LW[k].x = cx * cs; LW[k].y = cx * sn; }
+                if (wE) { sincos_r<R>(dx * __ldcg(A.a + n), &sn, &cs); LE[k].x = cx * cs; LE[k].y = cx * sn; }
+                if (wS) { sincos_r<R>(dy * __ldcg(A.b + n - P), &sn, &cs); LS[k].x = cy * cs; LS[k].y = cy * sn; }
+                if (wN) { sincos_r<R>(dy * __ldcg(A.b + n), &sn, &cs); LN[k].x = cy * cs; LN[k].y = cy * sn; }
                 const R e = A.epsf ? A.epsf[n] : A.eps;
                 const R nwx = (wW ? (R)1 : (R)0) + (wE ? (R)1 : (R)0), nwy = (wS ? (R)1 : (R)0) + (wN ? (R)1 : (R)0);
                 const R D = (R)1.0 + dt * (qq.x * qq.x + qq.y * qq.y - e + (idx2 * nwx + idy2 * nwy));
@@ -117,14 +155,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_td_small(const __grid_constan
             }
             int res = SVL_MAX_SWEEPS;
             for (int s = 0; s < SVL_MAX_SWEEPS; s++) {
-                const C *in = s == 0 ? B0 : ((s & 1) ? S1 : S2);
-                C *out = (s & 1) ? S2 : S1;
+                const C *in = (s & 1) ? X1 : X0;
+                C *out = (s & 1) ? X0 : X1, *olo = (s & 1) ? lo0 : lo1, *ohi = (s & 1) ? hi0 : hi1;
                 double rmax = 0.0;
 #pragma unroll
                 for (int k = 0; k < NPT; k++) {
                     if (!ok[k]) continue;
-                    const int n = off[k];
-                    const C pw = ts_ld(in + n - 1), pe = ts_ld(in + n + 1), pS = ts_ld(in + n - P), pN = ts_ld(in + n + P);
+                    const int l = L[k];
+                    const C pw = in[l - 1], pe = in[l + 1], pS = in[l - Nx], pN = in[l + Nx];
                     // W,S use (c + i s) psi, E,N use (c - i s) psi (the order of psi_tile.cu)
                     R ax = q[k].x, ay = q[k].y;
                     ax = fma_r(LW[k].x, pw.x, ax);  ay = fma_r(LW[k].x, pw.y, ay);
@@ -137,7 +175,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_td_small(const __grid_constan
                     ax = fma_r(LN[k].y, pN.y, ax);  ay = fma_r(-LN[k].y, pN.x, ay);
                     C nx;
                     nx.x = ax * di[k]; nx.y = ay * di[k];
-                    out[n] = nx;
+                    put(out, olo, ohi, k, nx);
                     rmax = fmax(rmax, (double)fmax(fabs(nx.x - own[k].x), fabs(nx.y - own[k].y)));
                     own[k] = nx;
                 }
@@ -145,19 +183,20 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_td_small(const __grid_constan
                 if (ts_stop(r, A.stop_psi, fp32)) { res = s + 1; break; }
             }
             npsi += res;
-            const int w = ((res - 1) & 1) ? 2 : 1;           // role that holds the result
-            const int t0 = pr[0]; pr[0] = pr[w]; pr[w] = t0;
+#pragma unroll
+            for (int k = 0; k < NPT; k++)
+                if (ok[k]) A.psi[off[k]] = own[k];
             rand_t += 1u;                                    // td.py:204
+            cl.sync();                                       // the new psi is visible to the whole cluster
         }
         // ============================ A solve (td.h:311-463; drivers td.py:252-325; quirk Q1)
         if (A.solveA) {
-            const C *psi = A.psi[pr[0]];
-            R *B0a = A.a[ar[0]], *B0b = A.b[ar[0]], *S1a = A.a[ar[1]], *S1b = A.b[ar[1]], *S2a = A.a[ar[2]], *S2b = A.b[ar[2]];
+            // the (a, b) pair of a node travels as one complex-sized element
+            load_state([&](int o) { C v; v.x = __ldcg(A.a + o); v.y = __ldcg(A.b + o); return v; });
             const R dt_rho = dt * A.rho, dtrk = dt_rho * A.kappa2;
             const R inv_da = (R)1.0 / ((R)1.0 + (R)2.0 * dtrk * idy2), inv_db = (R)1.0 / ((R)1.0 + (R)2.0 * dtrk * idx2);
             const bool noise = A.lang_A > (R)1.0e-32;
-            C p0[NPT], pE[NPT], pN[NPT];
-            R qa[NPT], qb[NPT], owa[NPT], owb[NPT], ca[NPT], cb[NPT];
+            C p0[NPT], pE[NPT], pN[NPT], qab[NPT], own[NPT], cab[NPT];
             // boundary terms of an edge (td.h:375-377, 421-423): recomputed where needed, two compares each
             auto bnd_a = [&](int j, R &rh, R &dd) {
                 rh = 0; dd = 1;
@@ -167,107 +206,93 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_td_small(const __grid_constan
             auto bnd_b = [&](int i, R &rh, R &dd) {
                 rh = 0; dd = 1;
                 if (i == 0) { rh = -(R)2.0 * A.kappa2 * A.H * idx; dd = 2; }
-                else if (i + 1 == g.Nx) { rh = (R)2.0 * A.kappa2 * A.H * idx; dd = 2; }
+                else if (i + 1 == Nx) { rh = (R)2.0 * A.kappa2 * A.H * idx; dd = 2; }
             };
 #pragma unroll
             for (int k = 0; k < NPT; k++) {
                 C z; z.x = 0; z.y = 0;
-                p0[k] = z; pE[k] = z; pN[k] = z;
-                qa[k] = 0; qb[k] = 0; owa[k] = 0; owb[k] = 0; ca[k] = 0; cb[k] = 0;
+                p0[k] = z; pE[k] = z; pN[k] = z; qab[k] = z; own[k] = z; cab[k] = z;
                 if (!ok[k]) continue;
                 const int n = off[k], i = ci[k], j = cj[k];
-                p0[k] = ts_ld(psi + n); pE[k] = ts_ld(psi + n + 1); pN[k] = ts_ld(psi + n + P);
-                if (i < g.Nx - 1) {
-                    owa[k] = ts_ld(B0a + n);
-                    qa[k] = owa[k];
-                    if (noise) qa[k] += A.lang_A * (rand_1<R>((uint32_t)i + (uint32_t)(g.Nx - 1) * (uint32_t)j, rand_t) - (R)0.5);
-                }
-                if (j < g.Ny - 1) {
-                    owb[k] = ts_ld(B0b + n);
-                    qb[k] = owb[k];
-                    if (noise)
-                        qb[k] += A.lang_A * (rand_2<R>((uint32_t)((size_t)(g.Nx - 1) * g.Ny) + (uint32_t)i + (uint32_t)g.Nx * (uint32_t)j, rand_t) - (R)0.5);
-                }
+                p0[k] = __ldcg(A.psi + n); pE[k] = __ldcg(A.psi + n + 1); pN[k] = __ldcg(A.psi + n + P);
+                own[k] = X0[L[k]];
+                if (i >= Nx - 1) own[k].x = 0;               // no a-edge in the last column, no b-edge in the last row
+                if (j >= g.Ny - 1) own[k].y = 0;
+                qab[k] = own[k];
+                if (noise && i < Nx - 1) qab[k].x += A.lang_A * (rand_1<R>((uint32_t)i + (uint32_t)(Nx - 1) * (uint32_t)j, rand_t) - (R)0.5);
+                if (noise && j < g.Ny - 1)
+                    qab[k].y += A.lang_A * (rand_2<R>((uint32_t)((size_t)(Nx - 1) * g.Ny) + (uint32_t)i + (uint32_t)Nx * (uint32_t)j, rand_t) - (R)0.5);
             }
             int res = SVL_MAX_SWEEPS;
             for (int s = 0; s < SVL_MAX_SWEEPS; s++) {
-                const R *ina = s == 0 ? B0a : ((s & 1) ? S1a : S2a), *inb = s == 0 ? B0b : ((s & 1) ? S1b : S2b);
-                R *oa = (s & 1) ? S2a : S1a, *ob = (s & 1) ? S2b : S1b;
+                const C *in = (s & 1) ? X1 : X0;
+                C *out = (s & 1) ? X0 : X1, *olo = (s & 1) ? lo0 : lo1, *ohi = (s & 1) ? hi0 : hi1;
                 double rmax = 0.0;
 #pragma unroll
                 for (int k = 0; k < NPT; k++) {
                     if (!ok[k]) continue;
-                    const int n = off[k], i = ci[k], j = cj[k];
+                    const int l = L[k], i = ci[k], j = cj[k];
                     const unsigned f = fl[k];
-                    R rha, dda, rhb, ddb;
-                    bnd_a(j, rha, dda);
-                    bnd_b(i, rhb, ddb);
-                    if (i < g.Nx - 1) {
-                        if (!(s & 1)) {      // the link phase of sweeps 2m and 2m+1 is iterate 2m (quirk Q1)
-                            R jl = 0;
-                            if (f & (NF_PM | NF_PP)) jl = idx * js_link<R, C>(p0[k], dx * owa[k], pE[k]);
-                            ca[k] = qa[k] + dt_rho * (jl + rha);
-                        }
-                        R lo = 0, hi = 0;
-                        if (j > 0) lo = idy2 * ts_ld(ina + n - P) - idxy * ts_ld(inb + n - P) + idxy * ts_ld(inb + n - P + 1);
-                        if (j + 1 < g.Ny) hi = idy2 * ts_ld(ina + n + P) + idxy * owb[k] - idxy * ts_ld(inb + n + 1);
-                        const R nx = (ca[k] + dtrk * dda * (lo + hi)) * inv_da;
-                        oa[n] = nx;
-                        rmax = fmax(rmax, fabs((double)(nx - owa[k])));
-                        // own a-value of the INPUT iterate is still needed by the b-edge below: keep it until then
-                        const R olda = owa[k];
-                        owa[k] = nx;
-                        if (j < g.Ny - 1) {
-                            if (!(s & 1)) {
-                                R jl = 0;
-                                if (f & (NF_MP | NF_PP)) jl = idy * js_link<R, C>(p0[k], dy * owb[k], pN[k]);
-                                cb[k] = qb[k] + dt_rho * (jl + rhb);
-                            }
-                            R lo2 = 0, hi2 = 0;
-                            if (i > 0) lo2 = idx2 * ts_ld(inb + n - 1) - idxy * ts_ld(ina + n - 1) + idxy * ts_ld(ina + n - 1 + P);
-                            if (i + 1 < g.Nx) hi2 = idx2 * ts_ld(inb + n + 1) + idxy * olda - idxy * ts_ld(ina + n + P);
-                            const R nb = (cb[k] + dtrk * ddb * (lo2 + hi2)) * inv_db;
-                            ob[n] = nb;
-                            rmax = fmax(rmax, fabs((double)(nb - owb[k])));
-                            owb[k] = nb;
-                        }
-                    } else if (j < g.Ny - 1) {       // last column: only the b-edge exists
-                        if (!(s & 1)) {
-                            R jl = 0;
-                            if (f & (NF_MP | NF_PP)) jl = idy * js_link<R, C>(p0[k], dy * owb[k], pN[k]);
-                            cb[k] = qb[k] + dt_rho * (jl + rhb);
-                        }
-                        R lo2 = 0;
-                        if (i > 0) lo2 = idx2 * ts_ld(inb + n - 1) - idxy * ts_ld(ina + n - 1) + idxy * ts_ld(ina + n - 1 + P);
-                        const R nb = (cb[k] + dtrk * ddb * (lo2 + (R)0)) * inv_db;
-                        ob[n] = nb;
-                        rmax = fmax(rmax, fabs((double)(nb - owb[k])));
-                        owb[k] = nb;
+                    C nx = own[k];
+                    if (!(s & 1)) {          // the link phase of sweeps 2m and 2m+1 is iterate 2m (quirk Q1)
+                        R rha, dda, rhb, ddb, jl = 0;
+                        bnd_a(j, rha, dda);
+                        bnd_b(i, rhb, ddb);
+                        if (f & (NF_PM | NF_PP)) jl = idx * js_link<R, C>(p0[k], dx * own[k].x, pE[k]);
+                        cab[k].x = qab[k].x + dt_rho * (jl + rha);
+                        jl = 0;
+                        if (f & (NF_MP | NF_PP)) jl = idy * js_link<R, C>(p0[k], dy * own[k].y, pN[k]);
+                        cab[k].y = qab[k].y + dt_rho * (jl + rhb);
                     }
+                    if (i < Nx - 1) {
+                        R rh, dd, lo = 0, hi = 0;
+                        bnd_a(j, rh, dd);
+                        if (j > 0) lo = idy2 * in[l - Nx].x - idxy * in[l - Nx].y + idxy * in[l - Nx + 1].y;
+                        if (j + 1 < g.Ny) hi = idy2 * in[l + Nx].x + idxy * own[k].y - idxy * in[l + 1].y;
+                        nx.x = (cab[k].x + dtrk * dd * (lo + hi)) * inv_da;
+                        rmax = fmax(rmax, fabs((double)(nx.x - own[k].x)));
+                    }
+                    if (j < g.Ny - 1) {
+                        R rh, dd, lo = 0, hi = 0;
+                        bnd_b(i, rh, dd);
+                        if (i > 0) lo = idx2 * in[l - 1].y - idxy * in[l - 1].x + idxy * in[l - 1 + Nx].x;
+                        if (i + 1 < Nx) hi = idx2 * in[l + 1].y + idxy * own[k].x - idxy * in[l + Nx].x;
+                        nx.y = (cab[k].y + dtrk * dd * (lo + hi)) * inv_db;
+                        rmax = fmax(rmax, fabs((double)(nx.y - own[k].y)));
+                    }
+                    put(out, olo, ohi, k, nx);
+                    own[k] = nx;
                 }
                 const double r = finish_sweep(rmax);
                 if (ts_stop(r, A.stop_A, fp32)) { res = s + 1; break; }
             }
             nA += res;
-            const int w = ((res - 1) & 1) ? 2 : 1;
-            const int t0 = ar[0]; ar[0] = ar[w]; ar[w] = t0;
+#pragma unroll
+            for (int k = 0; k < NPT; k++) {
+                if (!ok[k]) continue;
+                if (ci[k] < Nx - 1) A.a[off[k]] = own[k].x;
+                if (cj[k] < g.Ny - 1) A.b[off[k]] = own[k].y;
+            }
             rand_t += 1u;                                    // td.py:313
+            cl.sync();
         }
     }
-    if (gt == 0) {
-        A.out[0] = npsi; A.out[1] = nA; A.out[2] = pr[0]; A.out[3] = ar[0]; A.out[4] = (long long)rand_t;
-    }
+    if (rank == 0 && tid == 0) { A.out[0] = npsi; A.out[1] = nA; A.out[2] = (long long)rand_t; }
 }
 
 template <typename R, int NPT>
 static int ts_launch(svl_ctx *c, const SmallArgs<R> &A, int nctas, bool *handled) {
+    typedef typename V2<R>::type C;
     auto kern = k_td_small<R, NPT>;
+    const size_t smem = 2 * (size_t)(A.M + 2 * A.g.Nx) * sizeof(C) + 2 * TS_MAX_CTAS * sizeof(unsigned long long);
+    if (smem > 200 * 1024) return 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     if (nctas > 8) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
     }
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof(lc));
-    lc.gridDim = dim3(nctas); lc.blockDim = dim3(TS_THREADS); lc.stream = c->stream;
+    lc.gridDim = dim3(nctas); lc.blockDim = dim3(TS_THREADS); lc.stream = c->stream; lc.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = nctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -286,27 +311,31 @@ static int ts_run_t(svl_ctx *c, int Nt, double dt, int solveA, double eps, const
     typedef typename V2<R>::type C;
     const Geo &g = c->g;
     const long N = (long)g.Nx * g.Ny;
-    int npt = 0, nctas = 0;
-    for (int k = 1; k <= TS_MAX_NPT && !npt; k++)
-        for (int m = 1; m <= TS_MAX_CTAS; m *= 2)
-            if ((long)m * TS_THREADS * k >= N) { npt = k; nctas = m; break; }
+    // the fewest CTAs (a power of two up to 16: one cluster) whose share of nodes fits NPT <= 4 nodes per thread, and a
+    // share of at least one grid row (the halo of a CTA must lie in its direct neighbours)
+    int npt = 0, nctas = 0, M = 0;
+    for (int m = 1; m <= TS_MAX_CTAS && !npt; m *= 2) {
+        const long share = (N + m - 1) / m;
+        if (share > (long)TS_THREADS * TS_MAX_NPT) continue;
+        if (m > 1 && share < g.Nx) break;
+        nctas = m; M = (int)share; npt = (int)((share + TS_THREADS - 1) / TS_THREADS);
+    }
     if (!npt) return 0;
-    svl_buf *ps[2], *as[2];
-    for (int k = 0; k < 2; k++) { SVL_TRY(svl_scratch_node(c, k, &ps[k])); SVL_TRY(svl_scratch_edge(c, k, &as[k])); }
+    // more CTAs shorten a sweep as long as every CTA keeps at least one row and a full warp set busy
+    while (nctas < TS_MAX_CTAS && (N + 2 * nctas - 1) / (2 * nctas) >= g.Nx && (N + 2 * nctas - 1) / (2 * nctas) >= TS_THREADS) {
+        nctas *= 2; M = (int)((N + nctas - 1) / nctas); npt = (M + TS_THREADS - 1) / TS_THREADS;
+    }
     SmallArgs<R> A;
     memset(&A, 0, sizeof(A));
-    A.g = g; A.Nt = Nt; A.solveA = solveA;
+    A.g = g; A.Nt = Nt; A.solveA = solveA; A.M = M;
     A.dt = (R)dt; A.eps = (R)eps; A.kappa2 = (R)kappa2; A.rho = (R)rho; A.H = (R)H; A.lang_psi = (R)lang_psi; A.lang_A = (R)lang_A;
     A.stop_psi = stop_psi; A.stop_A = stop_A;
     A.epsf = epsf ? (const R *)epsf->p[0] : nullptr;
     A.nf = c->nf;
-    svl_buf *pb[3] = {psi, ps[0], ps[1]}, *abb[3] = {ab, as[0], as[1]};
-    for (int k = 0; k < 3; k++) { A.psi[k] = (C *)pb[k]->p[0]; A.a[k] = (R *)abb[k]->p[0]; A.b[k] = (R *)abb[k]->p[1]; }
+    A.psi = (C *)psi->p[0]; A.a = (R *)ab->p[0]; A.b = (R *)ab->p[1];
     A.rand_t = *rand_t;
-    A.ring = c->d_resid;
     long long *dout = (long long *)(c->d_result + 48);
     A.out = dout;
-    SVL_CHECK(cudaMemsetAsync(c->d_resid, 0, 4 * sizeof(unsigned long long), c->stream));
     switch (npt) {
         case 1: SVL_TRY((ts_launch<R, 1>(c, A, nctas, handled))); break;
         case 2: SVL_TRY((ts_launch<R, 2>(c, A, nctas, handled))); break;
@@ -316,11 +345,9 @@ static int ts_run_t(svl_ctx *c, int Nt, double dt, int solveA, double eps, const
     if (!*handled) return 0;
     c->stat_launches += 1;
     long long *hout = (long long *)(c->h_result + 48);
-    SVL_CHECK(cudaMemcpyAsync(hout, dout, 5 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    SVL_CHECK(cudaMemcpyAsync(hout, dout, 3 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     SVL_CHECK(cudaStreamSynchronize(c->stream));
-    if (hout[2] != 0) SVL_TRY(svl_swap(c, psi, pb[hout[2]]));
-    if (hout[3] != 0) SVL_TRY(svl_swap(c, ab, abb[hout[3]]));
-    *rand_t = (uint32_t)hout[4];
+    *rand_t = (uint32_t)hout[2];
     if (sweeps) { sweeps[0] += hout[0]; sweeps[1] += hout[1]; }
     c->stat_psi_sweeps += (double)hout[0]; c->stat_A_sweeps += (double)hout[1];
     if (Nt > 0) { c->pred_psi2 = c->pred_psi = (int)(hout[0] / Nt); c->pred_A2 = c->pred_A = (int)(hout[1] / Nt); }
