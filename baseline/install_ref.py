@@ -58,8 +58,24 @@ def prebuild_cubins():
         print(cubin_for(build_ref.reference_code(np.dtype(dt).type, Nx, Ny, dx, dy, rvl), out_dir=PREBUILT))
 
 
+def stage_acceptance_scripts():
+    """The reference's acceptance scripts (tests/at_*.py + common.py), copied verbatim next to the installed package
+    (baseline/_ref/ref_tests/, git-ignored) so that tests/test_gpu_dropin.py can run them UNMODIFIED against svirl_b200
+    on the GPU box, where /root/reference does not exist."""
+    import glob
+    src = os.path.join(REF, "tests")
+    if not os.path.isdir(src):
+        return
+    dst = os.path.join(DST, "ref_tests")
+    os.makedirs(dst, exist_ok=True)
+    for f in glob.glob(os.path.join(src, "at_*.py")) + [os.path.join(src, "common.py")]:
+        shutil.copyfile(f, os.path.join(dst, os.path.basename(f)))
+    print("staged", dst)
+
+
 if __name__ == "__main__":
     ok = install(force="--force" in sys.argv)
     print("installed" if ok else "skipped", DST)
     if ok:
         prebuild_cubins()
+        stage_acceptance_scripts()

@@ -269,6 +269,39 @@ class ScaleTD(object):
             return z, z.copy(), z.copy()
         return tuple(np.concatenate([o[k] for o in out]) for k in range(3))
 
+    # ---- slab checkpoints: one .npz per rank holding the rows this rank owns
+    def save_checkpoint(self, prefix):
+        """Write <prefix>.rank<r>of<w>.npz: the owned rows of psi, a, b (host layout [i, row]), the Langevin step counter
+        and the sweep counters.  Restoring it on the same decomposition continues the run bit for bit."""
+        self.synchronize()
+        j0, j1 = self.j0, self.j1
+        path = "%s.rank%dof%d.npz" % (prefix, self.rank, self.world)
+        np.savez(path, psi=self.psi_rows(j0, j1), a=self.a_rows(j0, j1), b=self.b_rows(j0, j1),
+                 rows=np.array([j0, j1]), shape=np.array([self.Nx, self.Ny]), rand_t=np.uint32(self.rand_t.value),
+                 sweeps=np.array([self.sweeps[0], self.sweeps[1]], dtype=np.int64),
+                 params=np.array([self.dx, self.dy, float(self.kappa), float(self.sigma), float(self.H), float(self.eps)]))
+        return path
+
+    def load_checkpoint(self, prefix):
+        """Inverse of save_checkpoint (same grid, same number of ranks); refreshes the halo rows from the neighbours."""
+        path = "%s.rank%dof%d.npz" % (prefix, self.rank, self.world)
+        with np.load(path) as d:
+            assert tuple(d["shape"]) == (self.Nx, self.Ny) and tuple(d["rows"]) == (self.j0, self.j1), "checkpoint of another decomposition"
+            j0, j1 = self.j0, self.j1
+            psi = np.ascontiguousarray(d["psi"].T.astype(self.ctype))
+            _lib.call("svl_h2d_rows", self._ctx, self.psi, 0, j0, j1, psi.ctypes.data_as(C.c_void_p))
+            a = np.ascontiguousarray(d["a"].T.astype(self.dtype))
+            _lib.call("svl_h2d_rows", self._ctx, self.ab, 0, j0, j1, a.ctypes.data_as(C.c_void_p))
+            b = np.ascontiguousarray(d["b"].T.astype(self.dtype))
+            if b.shape[0] > 0:
+                _lib.call("svl_h2d_rows", self._ctx, self.ab, 1, j0, j0 + b.shape[0], b.ctypes.data_as(C.c_void_p))
+            self.rand_t = C.c_uint32(int(d["rand_t"]))
+            self.sweeps[0], self.sweeps[1] = int(d["sweeps"][0]), int(d["sweeps"][1])
+        if self.world > 1:
+            _lib.call("svl_slab_exchange", self._ctx, self.psi)
+            _lib.call("svl_slab_exchange", self._ctx, self.ab)
+        _lib.call("svl_set_option", self._ctx, b"reset_prediction", 0)
+
     def close(self):
         if getattr(self, "_ctx", None):
             lib = _lib.load()

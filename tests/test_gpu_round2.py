@@ -137,3 +137,26 @@ def test_cg_two_pass_iteration_equals_kernel_composition(case, shape):
     tol = (1e-7 if "kinf" not in case else 1e-10) if f64 else 3e-3
     for k in (3, 4, 5):
         assert np.abs(res[0][k] - res[1][k]).max() < tol
+
+
+@pytest.mark.parametrize("case", ["f64_k2", "f32_kinf"])
+def test_scale_driver_checkpoint_restart_is_bitwise(case, tmp_path):
+    """a slab checkpoint (.npz) restored into a fresh driver continues the run bit for bit
+    (fields, Langevin counter, sweep counts)."""
+    from svirl_b200.scale import ScaleTD
+    dtype = np.float64 if case.startswith("f64") else np.float32
+    kw = dict(Nx=300, Ny=270, dx=0.5, dy=0.5, dtype=dtype, homogeneous_external_field=0.1, random_seed=1234,
+              gl_parameter=2.0 if "k2" in case else np.inf, normal_conductivity=10.0)
+    st = ScaleTD(band_rows=64, **kw)
+    st.td(0.1, 10)
+    st.save_checkpoint(str(tmp_path / "ck"))
+    st.td(0.1, 10)
+    want = (st.psi_rows(0, 270), st.a_rows(0, 270), st.b_rows(0, 269), st.sweeps[0], st.sweeps[1], st.rand_t.value)
+    st.close()
+    st2 = ScaleTD(band_rows=64, **dict(kw, random_seed=99))           # different initial state: everything comes from the file
+    st2.load_checkpoint(str(tmp_path / "ck"))
+    st2.td(0.1, 10)
+    assert (st2.sweeps[0], st2.sweeps[1], st2.rand_t.value) == want[3:]
+    assert np.array_equal(st2.psi_rows(0, 270), want[0])
+    assert np.array_equal(st2.a_rows(0, 270), want[1]) and np.array_equal(st2.b_rows(0, 269), want[2])
+    st2.close()
