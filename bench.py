@@ -413,9 +413,19 @@ def cg_cpu_baseline(wl):
 
 
 def bench_cg(args, wl, gl, par, N):
+    """--workload cfg4 / cfg4s / cfg4inf.  Under torchrun the grid is split into row slabs (strong scaling): the sums of an
+    iteration go over all ranks in rank order, the host line search is replicated."""
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     line = measure_cg(wl, gl, par, args.steps, args.warmup, args.line_search)
-    line["cpu_baseline"] = None if args.no_cpu_baseline else cg_cpu_baseline(wl)
-    print(json.dumps(line))
+    line["n_gpus"] = world
+    line["scaling"] = "strong" if world > 1 else "weak"
+    if world > 1:
+        line["roofline"]["frac"] /= world            # the bytes of an iteration are spread over the ranks
+        line["roofline"]["achieved"] /= world
+        line["roofline"]["note"] += "; per GPU (the grid is split over %d row slabs; three-pass iteration on slabs)" % world
+    if rank == 0:
+        line["cpu_baseline"] = None if (args.no_cpu_baseline or world > 1) else cg_cpu_baseline(wl)
+        print(json.dumps(line))
 
 
 def measure_td(wl, gl, par, steps, warmup):
@@ -614,7 +624,7 @@ def main():
     wl = workload(args.workload)
     if args.ny_mult > 1:
         wl = dict(wl, Ny=wl["Ny"] * args.ny_mult, name=wl["name"] + " (Ny x%d)" % args.ny_mult)
-    if world > 1 and args.impl == "ours" and not wl.get("scale"):
+    if world > 1 and args.impl == "ours" and not wl.get("scale") and not wl.get("cg"):
         wl = dict(wl, Ny=wl["Ny"] * world, name=wl["name"] + " x%d row slabs (Ny=%d)" % (world, wl["Ny"] * world))
     N = wl["Nx"] * wl["Ny"]
     cfgd = {"workload": wl["name"], "Nx": wl["Nx"], "Ny": wl["Ny"], "dt": 0.1, "seed": 1234,
