@@ -48,9 +48,11 @@ __device__ __forceinline__ void a_tma_load_2d(void *dst, const CUtensorMap *tm, 
         : "memory");
 }
 
-// Shared memory: [guard][psi C x NN][a0][b0][a1][b1][guard][barrier].  Tile-edge nodes read one
+// Shared memory: [guard][psi C x NN][a0][b0][guard][a1][b1][guard][barrier].  Tile-edge nodes read one
 // row / column beyond their array; those reads stay inside this block (guards) and only feed
-// tile-edge results, which are never used.
+// tile-edge results, which are never used.  The guard between b0 and a1 keeps such a read of the first sweep
+// away from the words the same sweep writes (a benign but real read/write hazard that compute-sanitizer's
+// racecheck reported in round 2).
 template <typename R, int TXE, int V, int NB>
 struct ASmem {
     typedef typename V2<R>::type C;
@@ -60,7 +62,7 @@ struct ASmem {
     static constexpr size_t off_psi = guard;
     static constexpr size_t off_a0 = off_psi + sizeof(C) * NN;
     static constexpr size_t off_b0 = off_a0 + sizeof(R) * NN;
-    static constexpr size_t off_a1 = off_b0 + sizeof(R) * NN;
+    static constexpr size_t off_a1 = off_b0 + sizeof(R) * NN + guard;
     static constexpr size_t off_b1 = off_a1 + sizeof(R) * NN;
     static constexpr size_t off_bar = off_b1 + sizeof(R) * NN + guard;
     static constexpr size_t total = off_bar + 16;
