@@ -94,7 +94,7 @@ def hole_tiling(Nx, Ny, dx=0.5, dy=0.5):
 def make_solver(wl, device_id=0, slab=None):
     from svirl_b200 import GLSolver
     kw = dict(Nx=wl["Nx"], Ny=wl["Ny"], dx=0.5, dy=0.5, dtype=wl["dtype"], gl_parameter=wl["kappa"],
-              normal_conductivity=wl["sigma"], homogeneous_external_field=wl["H"], random_seed=1234,
+              normal_conductivity=wl["sigma"], homogeneous_external_field=wl["H"], random_seed=wl.get("seed", 1234),
               device_id=device_id, slab=slab)
     if wl["tiling"]:
         kw["material_tiling"] = hole_tiling(wl["Nx"], wl["Ny"])
@@ -612,6 +612,8 @@ def main():
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (svl_set_option)")
     ap.add_argument("--ny-mult", type=int, default=1, help="multiply Ny (to run an N-GPU weak-scaling grid on fewer GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-instances", type=int, default=3,
+                    help="independent solver instances in flight in the end-to-end (host buffer) measurement; 1 = a single one")
     ap.add_argument("--also", default="cfg3,cfg4s,cfg1", help="extra single-GPU configs reported in `also` (default line only)")
     ap.add_argument("--no-extras", action="store_true", help="main line only: no parity / gpu_baseline / also / strong blocks")
     ap.add_argument("--line-search", default=None, choices=[None, "reference", "normalized", "native"])
@@ -671,15 +673,19 @@ def main():
             slab_bitwise = "error: %s" % (str(e)[:200],)
     gl = make_solver(wl, device_id=local, slab="auto" if world > 1 else None)
     par = gl.par
-    if args.psi_kernel is not None:
-        par.set_option("psi_kernel", args.psi_kernel)
-    if args.psi_k is not None:
-        par.set_option("psi_k", args.psi_k)
-    if args.a_kernel is not None:
-        par.set_option("a_kernel", args.a_kernel)
-    for kv in args.opt:
-        k, v = kv.split("=")
-        par.set_option(k, int(v))
+
+    def apply_opts(par_):
+        if args.psi_kernel is not None:
+            par_.set_option("psi_kernel", args.psi_kernel)
+        if args.psi_k is not None:
+            par_.set_option("psi_k", args.psi_k)
+        if args.a_kernel is not None:
+            par_.set_option("a_kernel", args.a_kernel)
+        for kv in args.opt:
+            k, v = kv.split("=")
+            par_.set_option(k, int(v))
+
+    apply_opts(par)
     td_kw = dict(dt=0.1)
     if wl.get("cg"):
         return bench_cg(args, wl, gl, par, N)
@@ -742,6 +748,43 @@ def main():
         e2e_s = float(t.item())
     e2e_val = N * e2e_steps / e2e_s
     replays = par.stat("replays")
+    e2e_blk = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(N * np.dtype(cdt).itemsize),
+               "d2h_bytes_per_step": int(N * np.dtype(cdt).itemsize), "steps": e2e_steps,
+               "api": "svl_h2d_rows + svl_td_run(1 step) + svl_d2h_rows on pinned host buffers"}
+
+    # ---- the same end-to-end loop for an ENSEMBLE of independent solver instances on this GPU, one host thread and
+    # one library context / stream each (svirl_b200.parallel.pipeline): upload, sweeps and download of different
+    # instances overlap; every instance-step still uploads its psi, runs one step and downloads the result
+    if world == 1 and args.e2e_instances > 1:
+        try:
+            from svirl_b200.parallel.pipeline import HostStepPipeline
+            M = args.e2e_instances
+            sols = [gl] + [make_solver(dict(wl, seed=wl.get("seed", 1234) + k), device_id=local) for k in range(1, M)]
+            for g_ in sols[1:]:
+                apply_opts(g_.par)
+                g_.solve.td(Nt=args.warmup, **td_kw)             # settles each instance's sweep prediction
+            pins = [(torch.empty_like(pin_in).pin_memory(), torch.empty_like(pin_in).pin_memory()) for _ in range(M)]
+            hin = [p_[0].numpy().view(cdt) for p_ in pins]
+            hout = [p_[1].numpy().view(cdt) for p_ in pins]
+            for g_, h_ in zip(sols, hin):
+                _lib.call("svl_d2h_rows", g_.par.ctx, h_.ctypes.data_as(C.c_void_p), g_.vars.order_parameter_h().handle,
+                          0, 0, int(wl["Ny"]))
+            pipe = HostStepPipeline(sols)
+            pipe.run(hin, hout, 2, **td_kw)                      # warm-up of the threads / pinned pages
+            torch.cuda.synchronize()
+            pipe_s = pipe.run(hin, hout, e2e_steps, **td_kw)
+            torch.cuda.synchronize()
+            e2e_blk = dict(e2e_blk, value=N * M * e2e_steps / pipe_s, steps=M * e2e_steps, instances=M,
+                           single_instance_value=e2e_val,
+                           api="svirl_b200.parallel.pipeline.HostStepPipeline over %d independent solver instances "
+                               "(one host thread + context + stream each); per instance-step: svl_h2d_rows (psi up), "
+                               "svl_td_run(1 step), svl_d2h_rows (psi down) on pinned host buffers; "
+                               "`single_instance_value` is the same loop with one instance" % M)
+            for g_ in sols[1:]:
+                g_.par.close()
+            del sols, pins, hin, hout, pipe
+        except Exception as e:                   # noqa: BLE001 -- keep the single-instance number
+            e2e_blk["ensemble_error"] = "%s: %s" % (type(e).__name__, str(e)[:300])
 
     # ---- BASELINE configs[4] on the same N GPUs: 32768^2 fp64 kappa=inf, STRONG scaling (all ranks take part)
     strong = None
@@ -788,6 +831,7 @@ def main():
             # (a fresh solver) against the psi the reference kernel just produced on the host
             try:
                 g2 = make_solver(wl, device_id=local)
+                apply_opts(g2.par)                   # the kernel variant that was timed
                 g2.solve.td(Nt=nst, **td_kw)
                 got = g2.flatten_array(g2.vars.order_parameter)
                 ref = info["psi"]
@@ -813,9 +857,7 @@ def main():
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if wl["dtype"] is np.float32 else "f64", "data": "synthetic", "config": cfgd,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(N * np.dtype(cdt).itemsize),
-                    "d2h_bytes_per_step": int(N * np.dtype(cdt).itemsize), "steps": e2e_steps,
-                    "api": "svl_h2d_rows + svl_td_run(1 step) + svl_d2h_rows on pinned host buffers"},
+            "e2e": e2e_blk,
             "gpu_launches": int(launches), "replays": replays,
             "psi_kernel": int(args.psi_kernel) if args.psi_kernel is not None else None,
             "parity": parity, "gpu_baseline": gpu_baseline, "slab_bitwise": slab_bitwise, "also": also, "strong": strong}

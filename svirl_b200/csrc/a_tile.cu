@@ -20,7 +20,7 @@
 #include <cuda.h>
 #include <type_traits>
 
-int svl_tma_map(CUtensorMap *out, CUtensorMapDataType dt, const void *base, size_t width, size_t rows,
+int svl_tma_map(svl_ctx *c, CUtensorMap *out, CUtensorMapDataType dt, const void *base, size_t width, size_t rows,
                 size_t pitch_bytes, int box_w, int box_h);   // psi_tile.cu
 
 struct ATileArgs {
@@ -315,9 +315,9 @@ static int launch_a_tile_t(svl_ctx *c, ATileArgs &A, const void *psi, const void
     const int cmul = dbl ? 2 : 1;
     size_t pr = (size_t)g.P * sizeof(R), pc = (size_t)g.P * sizeof(C);
     CUtensorMap tm[3];
-    SVL_TRY(svl_tma_map(&tm[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, psi, (size_t)g.Nx * cmul, g.rows, pc, TXE * cmul, S::EY));
-    SVL_TRY(svl_tma_map(&tm[1], rt, a, g.Nx, g.rows, pr, TXE, S::EY));
-    SVL_TRY(svl_tma_map(&tm[2], rt, b, g.Nx, g.rows, pr, TXE, S::EY));
+    SVL_TRY(svl_tma_map(c, &tm[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, psi, (size_t)g.Nx * cmul, g.rows, pc, TXE * cmul, S::EY));
+    SVL_TRY(svl_tma_map(c, &tm[1], rt, a, g.Nx, g.rows, pr, TXE, S::EY));
+    SVL_TRY(svl_tma_map(c, &tm[2], rt, b, g.Nx, g.rows, pr, TXE, S::EY));
     const int ntx_ = (g.Nx + TX - 1) / TX, nty_ = (g.j1 - g.j0 + TYO - 1) / TYO, rows_ = g.j1 - g.j0;
     A.push_expect[0] = A.push_expect[1] = 0;
     for (int by = 0; by < nty_; by++) {

@@ -107,6 +107,10 @@ extern "C" int svl_create(svl_ctx **out, int device_id, int Nx, int Ny, double d
     }
     c->opt_psi_kernel = 2;
     c->opt_psi_k = 4;
+    {   // fp32 link variables of the tile kernel: polynomial sincos (0) or MUFU (1); see psi_tile.cu
+        const char *e = getenv("SVL_PSI_LINKS");
+        c->opt_psi_links = e ? atoi(e) : 0;
+    }
     c->opt_tma = 1;
     c->opt_graphs = 1;
     c->opt_a_kernel = 2;
@@ -128,6 +132,12 @@ extern "C" int svl_destroy(svl_ctx *c) {
     }
     if (c->cg_s_node) svl_free(c, c->cg_s_node);
     if (c->cg_s_edge) svl_free(c, c->cg_s_edge);
+    // peer mappings first: the neighbours' arenas and boards opened over CUDA IPC
+    for (int s = 0; s < 2; s++)
+        if (c->ipc_base[s]) cudaIpcCloseMemHandle(c->ipc_base[s]);
+    for (int r = 0; r < c->board_world; r++)
+        if (r != c->board_rank && c->board_peer[r]) cudaIpcCloseMemHandle(c->board_peer[r]);
+    svl_tma_forget(c, nullptr);
     cudaFree(c->arena);
     cudaFree(c->board);
     cudaFree(c->nf); cudaFree(c->d_result); cudaFreeHost(c->h_result);
@@ -178,6 +188,7 @@ extern "C" int svl_set_option(svl_ctx *c, const char *name, int v) {
     SVL_REQUIRE(c && name, "null argument");
     if (!strcmp(name, "psi_kernel")) c->opt_psi_kernel = v;
     else if (!strcmp(name, "psi_k")) { SVL_REQUIRE(v >= 1 && v <= SVL_HALO, "psi_k out of range"); c->opt_psi_k = v; }
+    else if (!strcmp(name, "psi_links")) c->opt_psi_links = v;         // fp32 tile kernel: 1 = link variables by MUFU sin/cos (psi_tile.cu)
     else if (!strcmp(name, "tma")) c->opt_tma = v;
     else if (!strcmp(name, "graphs")) c->opt_graphs = v;
     else if (!strcmp(name, "spin_timeout_ms")) c->spin_limit = (long long)v * 2000000ll;   // ~2 GHz clock64 ticks; 0 = wait forever
@@ -281,6 +292,8 @@ extern "C" int svl_alloc(svl_ctx *c, int kind, size_t n, int elem_size, svl_buf 
 extern "C" int svl_free(svl_ctx *c, svl_buf *b) {
     if (!b) return 0;
     if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    svl_tma_forget(c, b->p[0]);
+    if (b->p[1]) svl_tma_forget(c, b->p[1]);
     if (!b->borrowed) { cudaFree(b->p[0]); cudaFree(b->p[1]); }
     delete b;
     return 0;

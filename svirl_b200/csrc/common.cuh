@@ -96,7 +96,7 @@ struct svl_ctx {
     // vortex candidates
     long long *d_cand; double *d_candv; unsigned long long *d_ncand; size_t cand_cap;
     // options / stats
-    int opt_psi_kernel, opt_psi_k, opt_tma, opt_graphs, opt_a_kernel, opt_cg_fused, opt_resid_board, opt_slab_nocomm, opt_slab_split, opt_cg_slabs;
+    int opt_psi_kernel, opt_psi_k, opt_psi_links, opt_tma, opt_graphs, opt_a_kernel, opt_cg_fused, opt_resid_board, opt_slab_nocomm, opt_slab_split, opt_cg_slabs;
     int pred_psi, pred_A;          // sweep counts of the previous solve
     int pred_psi2, pred_A2;        // ... and of the one before (trend)
     double stat_launches, stat_replays, stat_psi_sweeps, stat_A_sweeps;
@@ -129,6 +129,8 @@ struct svl_ctx {
     // waiting kernel raises *d_err (host-mapped pinned word) and carries on; the host turns it into an error
     long long spin_limit;          // clock64 cycles, 0 = unbounded
     int *h_err, *d_err;
+    void *tma_cache;               // tensor-map descriptors of this context's planes (psi_tile.cu)
+    void *ipc_base[2];             // neighbours' arenas as mapped by cudaIpcOpenMemHandle (closed by svl_destroy)
 };
 
 // what a kernel needs to bound a spin wait on a peer
@@ -147,6 +149,8 @@ int svl_launch_psi_sweep(svl_ctx *c, double dt, double eps, const svl_buf *epsf,
 int svl_launch_a_sweep(svl_ctx *c, double dt, double kappa2, double rho, double H, const svl_buf *psi,
                        const svl_buf *ph, const svl_buf *rhs, const svl_buf *ab, svl_buf *out,
                        double lang_c, uint32_t rand_t, int write_rhs, unsigned long long *resid_slot);
+// psi_tile.cu
+void svl_tma_forget(svl_ctx *c, const void *base);             // drop cached tensor maps of a plane (nullptr: all)
 // reduce.cu
 int svl_ensure_partials(svl_ctx *c, size_t n);
 int svl_finish_sum(svl_ctx *c, int nblocks, int nv, double scale, double *out_host);  // partials[nblocks*nv] -> host

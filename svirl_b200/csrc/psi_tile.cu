@@ -75,7 +75,24 @@ struct TileSmem {
 // Persistent CTAs: each loops over tiles tile = blockIdx.x, +gridDim.x, ...; the TMA boxes of the
 // next tile are issued as soon as this tile's constants are in registers, so the load overlaps the
 // K sweeps.
-template <typename R, int K, int TXE, int V, int NB, bool EPS, bool SLAB>
+// Link variable cos/sin of the tile kernel.  LINKS = 0: the library's polynomial sincos (<= 2 ulp).
+// LINKS = 1 (fp32 only, option psi_links): two-term Cody-Waite reduction by 2 pi + the hardware's
+// sin.approx / cos.approx (SASS MUFU.SIN / MUFU.COS): 7 instructions instead of 29 per link, max abs
+// error ~6e-7 -- the size of the rounding error of the fp32 phase d*A itself once |d*A| > 8.
+template <typename R, int LINKS>
+__device__ __forceinline__ void link_sincos(R x, R *s, R *c) { sincos_r<R>(x, s, c); }
+template <>
+__device__ __forceinline__ void link_sincos<float, 1>(float x, float *s, float *c) {
+    // no large-argument branch: one FMA rounding for any |x| < 2^23, where the fp32 phase itself is already
+    // uncertain by more than a radian
+    const float j = rintf(x * 0.15915494309189535f);
+    float r = fmaf(j, -6.2831854820251465f, x);          // 2 pi = 6.2831854820251465 - 1.7484556000744883e-07
+    r = fmaf(j, 1.7484556000744883e-07f, r);
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(*s) : "f"(r));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(*c) : "f"(r));
+}
+
+template <typename R, int K, int TXE, int V, int NB, bool EPS, bool SLAB, int LINKS>
 __global__ void __launch_bounds__(TXE *NB, (sizeof(R) == 4 ? 2 : 1))
 k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorMap tm_psi,
            const __grid_constant__ CUtensorMap tm_rhs, const __grid_constant__ CUtensorMap tm_a,
@@ -165,6 +182,18 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
     __shared__ unsigned int sm_rmax[K];      // per-sweep max-norm update of this CTA (bit patterns of floats/doubles >= 0)
     __shared__ unsigned long long sm_rmax64[K];
     if (tid < K) { sm_rmax[tid] = 0u; sm_rmax64[tid] = 0ull; }
+    // what the four "cell is material" bits of a node mean for its update, tabulated once per CTA: E / N link
+    // weights (0 or dt/d^2), the neighbour-count term of the diagonal, node active (1 or 0); td.h:48-116
+    __shared__ __align__(16) R s_fl[16][4];
+    if (tid < 16) {
+        const unsigned f = tid;
+        const R nwx = ((f & (NF_MM | NF_MP)) ? (R)1 : (R)0) + ((f & (NF_PM | NF_PP)) ? (R)1 : (R)0);
+        const R nwy = ((f & (NF_MM | NF_PM)) ? (R)1 : (R)0) + ((f & (NF_MP | NF_PP)) ? (R)1 : (R)0);
+        s_fl[f][0] = (f & (NF_PM | NF_PP)) ? cx : (R)0;
+        s_fl[f][1] = (f & (NF_MP | NF_PP)) ? cy : (R)0;
+        s_fl[f][2] = idx2 * nwx + idy2 * nwy;
+        s_fl[f][3] = f ? (R)1 : (R)0;
+    }
     uint32_t phase = 0;
 
     for (; tile < ntiles; tile += gridDim.x) {           // `tile` counts positions in the processing order
@@ -186,6 +215,26 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
         phase ^= 1;
         __syncthreads();      // also: everybody is done with the previous tile's exchange buffers
 
+        // ---- Langevin noise (td.h:92-101): folded into the staged right-hand side by a pass of its own, so that
+        // the unrolled constants loop below carries no noise code (each thread touches its own nodes only)
+        const bool rhs_is_psi = A.same_rhs && !A.noise;
+        if (A.noise) {
+            const bool xin0 = (x >= 0 && x < g.Nx);
+#pragma unroll 1
+            for (int v = 0; v < V; v++) {
+                const int r = r0 + v, si = r * TXE + col;
+                C qq = A.same_rhs ? ((const C *)(smem + S::st_psi))[si] : ((const C *)(smem + S::st_rhs))[si];
+                const unsigned f = xin0 ? (smem + S::st_nf)[r * NFW + nfd + col] : 0u;
+                if (f) {
+                    uint32_t nn = (uint32_t)x + (uint32_t)g.Nx * (uint32_t)(yg0 + r);
+                    qq.x += lang * (rand_1<R>(nn, A.rand_t) - (R)0.5);
+                    qq.y += lang * (rand_2<R>(nn, A.rand_t) - (R)0.5);
+                }
+                ((C *)(smem + S::st_rhs))[si] = qq;
+            }
+            // the next tile's TMA boxes (async proxy) overwrite what this thread just wrote through the generic proxy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
         // ---- per-node constants into registers
         C psi[V], q[V], La[V], Lb[V];
         R di[V];
@@ -195,37 +244,35 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
         if (r0 > 0) {         // S-link coefficient of the strip's first row = b-link of tile row r0-1
             const int si = (r0 - 1) * TXE + col;
             unsigned f = (smem + S::st_nf)[(r0 - 1) * NFW + nfd + col];
-            if (xin && (f & (NF_MP | NF_PP))) {
-                R sn, cs;
-                sincos_r<R>(dy * ((const R *)(smem + S::st_b))[si], &sn, &cs);
-                LbS0.x = cy * cs; LbS0.y = cy * sn;
-            }
+            if (!xin) f = 0;
+            const R wN = s_fl[f][1];
+            R sn, cs;
+            link_sincos<R, LINKS>(dy * ((const R *)(smem + S::st_b))[si], &sn, &cs);
+            LbS0.x = wN * cs; LbS0.y = wN * sn;
         }
 #pragma unroll
         for (int v = 0; v < V; v++) {
             const int r = r0 + v, si = r * TXE + col;
             C p0 = ((const C *)(smem + S::st_psi))[si];
-            C qq = A.same_rhs ? p0 : ((const C *)(smem + S::st_rhs))[si];
+            C qq = rhs_is_psi ? p0 : ((const C *)(smem + S::st_rhs))[si];
             R av = ((const R *)(smem + S::st_a))[si], bv = ((const R *)(smem + S::st_b))[si];
             unsigned f = (smem + S::st_nf)[r * NFW + nfd + col];
             R e = EPS ? ((const R *)(smem + S::st_eps))[si] : eps0;
             if (!xin) f = 0;
-            // branch-free: weights are 0/1 factors (inactive node: q = 0, links 0, 1/D irrelevant)
-            if (A.noise && f) {
-                uint32_t nn = (uint32_t)x + (uint32_t)g.Nx * (uint32_t)(yg0 + r);
-                qq.x += lang * (rand_1<R>(nn, A.rand_t) - (R)0.5);
-                qq.y += lang * (rand_2<R>(nn, A.rand_t) - (R)0.5);
+            R wE, wN, nw, act;
+            if (sizeof(R) == 4) {
+                const float4 w = *(const float4 *)&s_fl[f][0];
+                wE = w.x; wN = w.y; nw = w.z; act = w.w;
+            } else {
+                const double2 w0 = *(const double2 *)&s_fl[f][0], w1 = *(const double2 *)&s_fl[f][2];
+                wE = w0.x; wN = w0.y; nw = w1.x; act = w1.y;
             }
-            const R wE = (f & (NF_PM | NF_PP)) ? cx : (R)0, wN = (f & (NF_MP | NF_PP)) ? cy : (R)0;
-            const R act = f ? (R)1 : (R)0;
             R sn, cs;
             C la, lb;
-            sincos_r<R>(dx * av, &sn, &cs); la.x = wE * cs; la.y = wE * sn;
-            sincos_r<R>(dy * bv, &sn, &cs); lb.x = wN * cs; lb.y = wN * sn;
-            const R nwx = ((f & (NF_MM | NF_MP)) ? (R)1 : (R)0) + ((f & (NF_PM | NF_PP)) ? (R)1 : (R)0);
-            const R nwy = ((f & (NF_MM | NF_PM)) ? (R)1 : (R)0) + ((f & (NF_MP | NF_PP)) ? (R)1 : (R)0);
+            link_sincos<R, LINKS>(dx * av, &sn, &cs); la.x = wE * cs; la.y = wE * sn;
+            link_sincos<R, LINKS>(dy * bv, &sn, &cs); lb.x = wN * cs; lb.y = wN * sn;
             qq.x *= act; qq.y *= act;
-            const R D = (R)1.0 + dt * (qq.x * qq.x + qq.y * qq.y - e + (idx2 * nwx + idy2 * nwy));
+            const R D = (R)1.0 + dt * (qq.x * qq.x + qq.y * qq.y - e + nw);
             // inactive / out-of-domain nodes stay exactly 0 (td.h:117 writes psi_next = 0): D may vanish there
             // (dt*eps == 1), and 0 * inf would seed NaNs that the zero-weight links then spread
             const R d = f ? rcp_r(D) : (R)0;
@@ -242,12 +289,12 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
 #pragma unroll
         for (int v = 0; v < V; v++)
             if (cin && r0 + v >= K && r0 + v < EY - K && yg0 + r0 + v < g.j1) inmask |= 1u << v;
-        const C *src = xb0;
-        C *dst = xb1;
-#pragma unroll 1
-        for (int k = 0; k < K; k++) {          // rolled on purpose: the unrolled body would not fit the instruction cache
+        // One sweep: iterate `in` (registers; W/E neighbours and the strip ends from `src`) -> `out` (registers, and
+        // `dst` for the neighbouring threads unless it is the last sweep).  The k loop below is unrolled by two with
+        // the roles of the two register sets swapped, so no sweep ends with a register copy; it is not unrolled
+        // further because the body would not fit the instruction cache.
+        auto sweep = [&](const C(&in)[V], C(&out)[V], const C *src, C *dst, const int k) {
             R rm = 0;
-            C nx[V];
             const C below = src[(r0) * XW + col + 1];              // tile row r0-1
             const C above = src[(r0 + V + 1) * XW + col + 1];      // tile row r0+V
 #pragma unroll
@@ -255,8 +302,8 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
                 const int xi = (r0 + v + 1) * XW + col + 1;
                 const C pw = src[xi - 1], pe = src[xi + 1];
                 const C lw = sla[xi - 1];
-                const C pS = v > 0 ? psi[v - 1] : below;
-                const C pN = v < V - 1 ? psi[v + 1] : above;
+                const C pS = v > 0 ? in[v - 1] : below;
+                const C pN = v < V - 1 ? in[v + 1] : above;
                 const C ls = v > 0 ? Lb[v - 1] : LbS0;
                 // 16 chained FMAs: W,S use (c + i s) psi, E,N use (c - i s) psi
                 R ax = q[v].x, ay = q[v].y;
@@ -268,25 +315,38 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
                 ax = fma_r(-ls.y, pS.y, ax);    ay = fma_r(ls.y, pS.x, ay);
                 ax = fma_r(Lb[v].x, pN.x, ax);  ay = fma_r(Lb[v].x, pN.y, ay);
                 ax = fma_r(Lb[v].y, pN.y, ax);  ay = fma_r(-Lb[v].y, pN.x, ay);
-                nx[v].x = ax * di[v];
-                nx[v].y = ay * di[v];
+                out[v].x = ax * di[v];
+                out[v].y = ay * di[v];
             }
+            const bool more = k < K - 1;
 #pragma unroll
             for (int v = 0; v < V; v++) {
-                const int r = r0 + v;
                 if (inmask & (1u << v))
-                    rm = fmax(rm, fmax(fabs(nx[v].x - psi[v].x), fabs(nx[v].y - psi[v].y)));
-                psi[v] = nx[v];
-                if (k < K - 1) dst[(r + 1) * XW + col + 1] = nx[v];
+                    rm = fmax(rm, fmax(fabs(out[v].x - in[v].x), fabs(out[v].y - in[v].y)));
+                if (more) dst[(r0 + v + 1) * XW + col + 1] = out[v];
             }
             // warp max -> one shared atomicMax per warp and sweep (non-negative values order like their bits)
-            for (int o = 16; o > 0; o >>= 1) rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, o));
-            if ((tid & 31) == 0 && rm > (R)0) {
-                if (sizeof(R) == 4) atomicMax(&sm_rmax[k], __float_as_uint((float)rm));
-                else atomicMax(&sm_rmax64[k], (unsigned long long)__double_as_longlong((double)rm));
+            if (sizeof(R) == 4) {
+                const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint((float)rm));
+                if ((tid & 31) == 0 && wm) atomicMax(&sm_rmax[k], wm);
+            } else {
+                for (int o = 16; o > 0; o >>= 1) rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, o));
+                if ((tid & 31) == 0 && rm > (R)0) atomicMax(&sm_rmax64[k], (unsigned long long)__double_as_longlong((double)rm));
             }
-            if (k < K - 1) __syncthreads();
-            const C *tsw = src; src = dst; dst = (C *)tsw;
+            if (more) __syncthreads();
+        };
+        {
+            C nx[V];
+#pragma unroll 1
+            for (int k = 0; k + 1 < K; k += 2) {
+                sweep(psi, nx, xb0, xb1, k);
+                sweep(nx, psi, xb1, xb0, k + 1);
+            }
+            if (K & 1) {
+                sweep(psi, nx, xb0, xb1, K - 1);
+#pragma unroll
+                for (int v = 0; v < V; v++) psi[v] = nx[v];
+            }
         }
         // ---- write the interior (slabs: the first / last `depth` rows also go to the neighbours' halos)
         const int rows_own = g.j1 - g.j0;
@@ -365,34 +425,48 @@ struct TileIO {
 };
 
 // Tensor maps depend only on (base pointer, geometry, box): the three psi buffers rotate, so a
-// small cache avoids six driver encode calls per launch.
+// small cache avoids six driver encode calls per launch.  The cache belongs to the CONTEXT (contexts
+// may be driven from different host threads) and forgets a plane when its buffer is freed.
 struct MapKey { const void *base; int w, rows, box_w, box_h, dt; size_t pitch; };
 struct MapEnt { MapKey k; CUtensorMap tm; };
-int svl_tma_map(CUtensorMap *out, CUtensorMapDataType dt, const void *base, size_t width, size_t rows,
+struct MapCache { MapEnt e[64]; int n, next; };
+int svl_tma_map(svl_ctx *c, CUtensorMap *out, CUtensorMapDataType dt, const void *base, size_t width, size_t rows,
                 size_t pitch_bytes, int box_w, int box_h) {   // also used by a_tile.cu
-    static MapEnt cache[64];
-    static int n = 0, next = 0;
-    MapKey k = {base, (int)width, (int)rows, box_w, box_h, (int)dt, pitch_bytes};
-    for (int i = 0; i < n; i++)
-        if (!memcmp(&cache[i].k, &k, sizeof(k))) { *out = cache[i].tm; return 0; }
+    if (!c->tma_cache) c->tma_cache = calloc(1, sizeof(MapCache));
+    MapCache *mc = (MapCache *)c->tma_cache;
+    SVL_REQUIRE(mc, "out of host memory");
+    MapKey k;
+    memset(&k, 0, sizeof(k));
+    k.base = base; k.w = (int)width; k.rows = (int)rows; k.box_w = box_w; k.box_h = box_h; k.dt = (int)dt; k.pitch = pitch_bytes;
+    for (int i = 0; i < mc->n; i++)
+        if (!memcmp(&mc->e[i].k, &k, sizeof(k))) { *out = mc->e[i].tm; return 0; }
     CUtensorMap tm;
     SVL_TRY(t_make_map(&tm, dt, base, width, rows, pitch_bytes, box_w, box_h));
-    int slot = n < 64 ? n++ : (next++ % 64);
-    memset(&cache[slot].k, 0, sizeof(MapKey));
-    cache[slot].k = k; cache[slot].tm = tm;
+    int slot = mc->n < 64 ? mc->n++ : (mc->next++ % 64);
+    mc->e[slot].k = k; mc->e[slot].tm = tm;
     *out = tm;
     return 0;
 }
+// svl_free / svl_destroy: descriptors of a released plane must not outlive it (base == nullptr: all of them)
+void svl_tma_forget(svl_ctx *c, const void *base) {
+    if (!c || !c->tma_cache) return;
+    MapCache *mc = (MapCache *)c->tma_cache;
+    if (!base) { free(mc); c->tma_cache = nullptr; return; }
+    for (int i = 0; i < mc->n;) {
+        if (mc->e[i].k.base == base) mc->e[i] = mc->e[--mc->n];
+        else i++;
+    }
+}
 
-template <typename R, int K, int TXE, int V, int NB, bool EPS>
+template <typename R, int K, int TXE, int V, int NB, bool EPS, int LINKS>
 static int launch_tile_t(svl_ctx *c, TileArgs &A, const TileIO &io) {
     typedef typename V2<R>::type C;
     typedef TileSmem<R, K, TXE, V, NB, EPS> S;
     const Geo &g = c->g;
     constexpr int TX = TXE - 2 * S::H, TYO = S::EY - 2 * K;
     static_assert(TYO > 0 && TX > 0, "tile too small for this K");
-    auto kern = k_psi_tile<R, K, TXE, V, NB, EPS, false>;
-    auto kern_slab = k_psi_tile<R, K, TXE, V, NB, EPS, true>;       // with halo wait + in-kernel push
+    auto kern = k_psi_tile<R, K, TXE, V, NB, EPS, false, LINKS>;
+    auto kern_slab = k_psi_tile<R, K, TXE, V, NB, EPS, true, LINKS>;       // with halo wait + in-kernel push
     static int slots = 0;
     if (!slots) {
         int occ = 1, nsm = 148;
@@ -409,12 +483,12 @@ static int launch_tile_t(svl_ctx *c, TileArgs &A, const TileIO &io) {
     static_assert(TXE * 2 <= 256, "complex double box exceeds 256 elements");
     size_t pr = (size_t)g.P * sizeof(R), pc = (size_t)g.P * sizeof(C);
     CUtensorMap tm[6];
-    SVL_TRY(svl_tma_map(&tm[0], ct, io.psi, (size_t)g.Nx * cmul, g.rows, pc, TXE * cmul, S::EY));
-    SVL_TRY(svl_tma_map(&tm[1], ct, io.rhs, (size_t)g.Nx * cmul, g.rows, pc, TXE * cmul, S::EY));
-    SVL_TRY(svl_tma_map(&tm[2], rt, io.a, g.Nx, g.rows, pr, TXE, S::EY));
-    SVL_TRY(svl_tma_map(&tm[3], rt, io.b, g.Nx, g.rows, pr, TXE, S::EY));
-    SVL_TRY(svl_tma_map(&tm[4], rt, EPS ? io.epsf : io.a, g.Nx, g.rows, pr, TXE, S::EY));
-    SVL_TRY(svl_tma_map(&tm[5], CU_TENSOR_MAP_DATA_TYPE_UINT8, io.nf, g.Nx, g.rows, (size_t)g.P, S::NFW, S::EY));
+    SVL_TRY(svl_tma_map(c, &tm[0], ct, io.psi, (size_t)g.Nx * cmul, g.rows, pc, TXE * cmul, S::EY));
+    SVL_TRY(svl_tma_map(c, &tm[1], ct, io.rhs, (size_t)g.Nx * cmul, g.rows, pc, TXE * cmul, S::EY));
+    SVL_TRY(svl_tma_map(c, &tm[2], rt, io.a, g.Nx, g.rows, pr, TXE, S::EY));
+    SVL_TRY(svl_tma_map(c, &tm[3], rt, io.b, g.Nx, g.rows, pr, TXE, S::EY));
+    SVL_TRY(svl_tma_map(c, &tm[4], rt, EPS ? io.epsf : io.a, g.Nx, g.rows, pr, TXE, S::EY));
+    SVL_TRY(svl_tma_map(c, &tm[5], CU_TENSOR_MAP_DATA_TYPE_UINT8, io.nf, g.Nx, g.rows, (size_t)g.P, S::NFW, S::EY));
     const int ntx_ = (g.Nx + TX - 1) / TX, nty_ = (g.j1 - g.j0 + TYO - 1) / TYO, rows_ = g.j1 - g.j0;
     A.push_expect[0] = A.push_expect[1] = 0;
     int nlo = 0, nhi = 0;                                  // tile rows that feed the lo / hi push
@@ -465,15 +539,15 @@ static int launch_tile_t(svl_ctx *c, TileArgs &A, const TileIO &io) {
     return 0;
 }
 
-template <typename R, int TXE, int V, int NB, bool EPS>
+template <typename R, int TXE, int V, int NB, bool EPS, int LINKS>
 static int launch_tile_k(svl_ctx *c, int K, TileArgs &A, const TileIO &io) {
     switch (K) {
-        case 1: return launch_tile_t<R, 1, TXE, V, NB, EPS>(c, A, io);
-        case 2: return launch_tile_t<R, 2, TXE, V, NB, EPS>(c, A, io);
-        case 3: return launch_tile_t<R, 3, TXE, V, NB, EPS>(c, A, io);
-        case 4: return launch_tile_t<R, 4, TXE, V, NB, EPS>(c, A, io);
-        case 6: return launch_tile_t<R, 6, TXE, V, NB, EPS>(c, A, io);
-        case 8: return launch_tile_t<R, 8, TXE, V, NB, EPS>(c, A, io);
+        case 1: return launch_tile_t<R, 1, TXE, V, NB, EPS, LINKS>(c, A, io);
+        case 2: return launch_tile_t<R, 2, TXE, V, NB, EPS, LINKS>(c, A, io);
+        case 3: return launch_tile_t<R, 3, TXE, V, NB, EPS, LINKS>(c, A, io);
+        case 4: return launch_tile_t<R, 4, TXE, V, NB, EPS, LINKS>(c, A, io);
+        case 6: return launch_tile_t<R, 6, TXE, V, NB, EPS, LINKS>(c, A, io);
+        case 8: return launch_tile_t<R, 8, TXE, V, NB, EPS, LINKS>(c, A, io);
     }
     svl_set_error("psi_tile: K=%d not instantiated (1,2,3,4,6,8)", K);
     return 2;
@@ -501,9 +575,13 @@ int svl_launch_psi_tile(svl_ctx *c, int K, double dt, double eps, const svl_buf 
     }
     TileIO io = {psi->p[0], rhs->p[0], ab->p[0], ab->p[1], epsf ? epsf->p[0] : nullptr, c->nf};
     if (c->rsize == 4) {
-        if (epsf) return launch_tile_k<float, 64, 8, 4, true>(c, K, A, io);
-        return launch_tile_k<float, 64, 8, 4, false>(c, K, A, io);
+        if (c->opt_psi_links) {
+            if (epsf) return launch_tile_k<float, 64, 8, 4, true, 1>(c, K, A, io);
+            return launch_tile_k<float, 64, 8, 4, false, 1>(c, K, A, io);
+        }
+        if (epsf) return launch_tile_k<float, 64, 8, 4, true, 0>(c, K, A, io);
+        return launch_tile_k<float, 64, 8, 4, false, 0>(c, K, A, io);
     }
-    if (epsf) return launch_tile_k<double, 64, 4, 8, true>(c, K, A, io);
-    return launch_tile_k<double, 64, 4, 8, false>(c, K, A, io);
+    if (epsf) return launch_tile_k<double, 64, 4, 8, true, 0>(c, K, A, io);
+    return launch_tile_k<double, 64, 4, 8, false, 0>(c, K, A, io);
 }

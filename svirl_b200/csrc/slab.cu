@@ -199,6 +199,7 @@ extern "C" int svl_slab_connect(svl_ctx *c, const void *lo, int lo_j0, const voi
         const SlabHandle *h = (const SlabHandle *)hs[s];
         void *base = nullptr;
         SVL_CHECK(cudaIpcOpenMemHandle(&base, h->h, cudaIpcMemLazyEnablePeerAccess));
+        c->ipc_base[s] = base;
         for (int k = 0; k < 9; k++) c->peer[s][k] = (char *)base + h->off[k];
         c->peer_flags[s] = (unsigned long long *)((char *)base + h->off[9]);
         c->nb_rb[s] = j0s[s] - SVL_HALO;

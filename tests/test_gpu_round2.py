@@ -160,3 +160,37 @@ def test_scale_driver_checkpoint_restart_is_bitwise(case, tmp_path):
     assert np.array_equal(st2.psi_rows(0, 270), want[0])
     assert np.array_equal(st2.a_rows(0, 270), want[1]) and np.array_equal(st2.b_rows(0, 269), want[2])
     st2.close()
+
+
+def test_host_step_pipeline_equals_sequential_steps():
+    """Three solver instances driven by three host threads (upload, one step, download per instance-step,
+    svirl_b200/parallel/pipeline.py) end in the states the same instances reach one after the other, bit for bit:
+    contexts share nothing (per-context streams, scratch, tensor-map cache)."""
+    import ctypes as C
+    from svirl_b200 import GLSolver, _lib
+    from svirl_b200.parallel.pipeline import HostStepPipeline
+    Nx, Ny, nst = 300, 270, 4
+    mt = np.ones((Nx - 1, Ny - 1), dtype=bool)
+    mt[40:60, 30:50] = False
+
+    def make(seed):
+        return GLSolver(Nx=Nx, Ny=Ny, dx=0.5, dy=0.5, dtype=np.float32, gl_parameter=np.inf,
+                        homogeneous_external_field=0.1, random_seed=seed, material_tiling=mt)
+
+    seeds = [3, 4, 5]
+    want = []
+    for s in seeds:                                   # sequential: psi stays on the device
+        gl = make(s)
+        gl.solve.td(dt=0.1, Nt=nst)
+        want.append(gl.flatten_array(gl.vars.order_parameter).copy())
+        gl.par.close()
+    sols = [make(s) for s in seeds]
+    hin = [np.ascontiguousarray(g.flatten_array(g.vars.order_parameter)) for g in sols]
+    hout = [np.empty_like(h) for h in hin]
+    secs = HostStepPipeline(sols).run(hin, hout, nst, dt=0.1)
+    assert secs > 0
+    for k, g in enumerate(sols):
+        last = hout[k] if nst % 2 == 1 else hin[k]    # buffers swap roles every step
+        assert np.array_equal(last, want[k]), k
+        assert np.array_equal(g.flatten_array(g.vars.order_parameter), want[k]), k
+        g.par.close()
