@@ -107,9 +107,10 @@ extern "C" int svl_create(svl_ctx **out, int device_id, int Nx, int Ny, double d
     }
     c->opt_psi_kernel = 2;
     c->opt_psi_k = 4;
-    {   // fp32 link variables of the tile kernel: polynomial sincos (0) or MUFU (1); see psi_tile.cu
+    {   // fp32 link variables of the tile kernel: MUFU sin/cos after an exact reduction (1, default) or the
+        // polynomial sincos (0); see link_sincos in psi_tile.cu.  fp64 always uses the polynomial.
         const char *e = getenv("SVL_PSI_LINKS");
-        c->opt_psi_links = e ? atoi(e) : 0;
+        c->opt_psi_links = e ? atoi(e) : 1;
     }
     c->opt_tma = 1;
     c->opt_graphs = 1;

@@ -294,7 +294,6 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
         // the roles of the two register sets swapped, so no sweep ends with a register copy; it is not unrolled
         // further because the body would not fit the instruction cache.
         auto sweep = [&](const C(&in)[V], C(&out)[V], const C *src, C *dst, const int k) {
-            R rm = 0;
             const C below = src[(r0) * XW + col + 1];              // tile row r0-1
             const C above = src[(r0 + V + 1) * XW + col + 1];      // tile row r0+V
 #pragma unroll
@@ -319,19 +318,35 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
                 out[v].y = ay * di[v];
             }
             const bool more = k < K - 1;
-#pragma unroll
-            for (int v = 0; v < V; v++) {
-                if (inmask & (1u << v))
-                    rm = fmax(rm, fmax(fabs(out[v].x - in[v].x), fabs(out[v].y - in[v].y)));
-                if (more) dst[(r0 + v + 1) * XW + col + 1] = out[v];
-            }
-            // warp max -> one shared atomicMax per warp and sweep (non-negative values order like their bits)
+            // max-norm update over this thread's output nodes, one shared atomicMax per warp and sweep.  Non-negative
+            // values order like their bit patterns: fp32 reduces with REDUX on the bits; fp64 keeps the running maximum
+            // as a 64-bit integer as well (a double fmax is ~9 instructions on this machine, an integer one 4) and
+            // reduces the high and low words with two REDUX instead of five shuffle + fmax rounds.
             if (sizeof(R) == 4) {
+                R rm = 0;
+#pragma unroll
+                for (int v = 0; v < V; v++) {
+                    if (inmask & (1u << v))
+                        rm = fmax(rm, fmax(fabs(out[v].x - in[v].x), fabs(out[v].y - in[v].y)));
+                    if (more) dst[(r0 + v + 1) * XW + col + 1] = out[v];
+                }
                 const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint((float)rm));
                 if ((tid & 31) == 0 && wm) atomicMax(&sm_rmax[k], wm);
             } else {
-                for (int o = 16; o > 0; o >>= 1) rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, o));
-                if ((tid & 31) == 0 && rm > (R)0) atomicMax(&sm_rmax64[k], (unsigned long long)__double_as_longlong((double)rm));
+                unsigned long long rb = 0ull;
+#pragma unroll
+                for (int v = 0; v < V; v++) {
+                    const double ex = (double)(out[v].x - in[v].x), ey = (double)(out[v].y - in[v].y);
+                    const unsigned long long bx = ((unsigned long long)(__double2hiint(ex) & 0x7fffffff) << 32) | (unsigned)__double2loint(ex);
+                    const unsigned long long by = ((unsigned long long)(__double2hiint(ey) & 0x7fffffff) << 32) | (unsigned)__double2loint(ey);
+                    const unsigned long long bm = bx > by ? bx : by;
+                    rb = ((inmask & (1u << v)) && bm > rb) ? bm : rb;
+                    if (more) dst[(r0 + v + 1) * XW + col + 1] = out[v];
+                }
+                const unsigned hi = (unsigned)(rb >> 32);
+                const unsigned whi = __reduce_max_sync(0xffffffffu, hi);
+                const unsigned wlo = __reduce_max_sync(0xffffffffu, hi == whi ? (unsigned)rb : 0u);
+                if ((tid & 31) == 0 && (whi | wlo)) atomicMax(&sm_rmax64[k], ((unsigned long long)whi << 32) | wlo);
             }
             if (more) __syncthreads();
         };
