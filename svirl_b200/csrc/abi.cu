@@ -197,6 +197,7 @@ extern "C" int svl_set_option(svl_ctx *c, const char *name, int v) {
     else if (!strcmp(name, "cg_fused")) c->opt_cg_fused = v;
     else if (!strcmp(name, "resid_board")) c->opt_resid_board = v;
     else if (!strcmp(name, "slab_split")) c->opt_slab_split = v;
+    else if (!strcmp(name, "slab_bnd")) c->opt_slab_bnd = v;           // CTAs of the boundary launch: 0 = automatic, -1 = one per boundary tile (round-2a behaviour)
     else if (!strcmp(name, "cg_slabs")) c->opt_cg_slabs = v;           // no-op since round 2: CG / energy on row slabs is always on
     else if (!strcmp(name, "slab_nocomm")) c->opt_slab_nocomm = v;     // timing experiments only: ranks run uncoupled
     else if (!strcmp(name, "trace")) {                                 // diagnostics: record v launches from now on

@@ -34,6 +34,7 @@ struct TileArgs {
     int row0, nrow, row1, nrow1;   // tile rows this launch covers: [row0, row0+nrow) then [row1, row1+nrow1)
     int permute;                   // slabs, single launch: process the first / last tile row last
     int pdl_trigger;               // slabs, boundary launch: release the programmatic dependent (interior) launch at once
+    int defer_publish;             // slabs, boundary launch: a CTA fences and reports its pushed tiles ONCE, after its last tile
     SpinGuard sg;                  // bound of the spin waits (halo flags, TMA barrier)
     unsigned long long *trace;     // slabs, diagnostics: [0] first CTA start, [1] last CTA end, [2] longest flag wait,
                                    // [3] time the last flag wait ended (all %globaltimer ns), or null
@@ -128,6 +129,7 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
         return by * ntx + q % ntx;
     };
     bool flags_seen[2] = {false, false};                 // thread 0 only
+    int pend[2] = {0, 0};                                // slabs: tiles of this CTA whose push is not reported yet
     auto gtime = [&]() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
     auto wait_side = [&](int sdir) {
         if (flags_seen[sdir] || !(sdir == 0 ? A.has_lo : A.has_hi)) return;
@@ -377,17 +379,38 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
             }
         }
         if (plo || phi) {                        // CTA-uniform
-            __syncthreads();                     // all peer stores of the CTA issued ...
-            if (tid == 0) {
-                __threadfence_system();          // ... and made visible by ONE fence (grid-sync pattern)
-                for (int sdir = 0; sdir < 2; sdir++) {
-                    if (!(sdir == 0 ? plo : phi)) continue;
-                    unsigned int done = atomicAdd(&A.push.count[sdir], 1u);
-                    if ((int)done == A.push_expect[sdir] - 1) {
-                        A.push.count[sdir] = 0;
-                        __threadfence_system();
-                        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.push.flag[sdir]), "l"(A.push.epoch) : "memory");
+            if (A.defer_publish) {               // boundary launch: several tiles per CTA, one fence at the end
+                pend[0] += plo ? 1 : 0; pend[1] += phi ? 1 : 0;
+            } else {
+                __syncthreads();                     // all peer stores of the CTA issued ...
+                if (tid == 0) {
+                    __threadfence_system();          // ... and made visible by ONE fence (grid-sync pattern)
+                    for (int sdir = 0; sdir < 2; sdir++) {
+                        if (!(sdir == 0 ? plo : phi)) continue;
+                        unsigned int done = atomicAdd(&A.push.count[sdir], 1u);
+                        if ((int)done == A.push_expect[sdir] - 1) {
+                            A.push.count[sdir] = 0;
+                            __threadfence_system();
+                            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.push.flag[sdir]), "l"(A.push.epoch) : "memory");
+                        }
                     }
+                }
+            }
+        }
+    }
+    if (SLAB && (pend[0] | pend[1])) {           // CTA-uniform
+        // The system-scope fence behind peer stores takes ~10-20 us; a boundary CTA therefore pushes all its tiles
+        // first and pays it once (the launch gives the boundary tiles to a few CTAs, see launch_tile_t).
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            for (int sdir = 0; sdir < 2; sdir++) {
+                if (!pend[sdir]) continue;
+                unsigned int done = atomicAdd(&A.push.count[sdir], (unsigned int)pend[sdir]);
+                if ((int)done + pend[sdir] == A.push_expect[sdir]) {
+                    A.push.count[sdir] = 0;
+                    __threadfence_system();
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.push.flag[sdir]), "l"(A.push.epoch) : "memory");
                 }
             }
         }
@@ -526,16 +549,31 @@ static int launch_tile_t(svl_ctx *c, TileArgs &A, const TileIO &io) {
         TileArgs B = A;
         B.row0 = 0; B.nrow = nlo; B.row1 = nty_ - nhi; B.nrow1 = nhi;
         B.pdl_trigger = 1;
-        int nb = ntx_ * (nlo + nhi);
-        kern_slab<<<nb < slots ? nb : slots, TXE * NB, S::total, c->stream>>>(B, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]);
+        const int nb = ntx_ * (nlo + nhi), ni = ntx_ * (nty_ - nlo - nhi);
+        // The boundary tiles go to a FEW CTAs (each takes several tiles and fences once), the interior kernel gets the
+        // remaining slots, all resident from the start: a boundary CTA holds its slot through the system-scope fence,
+        // and an interior CTA that had to wait for that slot would finish its static share of tiles late.  Smallest
+        // boundary grid whose CTAs (tiles + ~3 tile times of fence) still finish well before the interior does.
+        int gb = nb < slots ? nb : slots;
+        if (c->opt_slab_bnd > 0) gb = c->opt_slab_bnd < gb ? c->opt_slab_bnd : gb;
+        else if (c->opt_slab_bnd == 0) {
+            for (int t = 4; t < gb; t++) {
+                const double tb = (double)((nb + t - 1) / t) + 3.0, ti = (double)ni / (double)(slots - t);
+                if (slots - t > 0 && tb <= 0.8 * ti) { gb = t; break; }
+            }
+        }
+        B.defer_publish = 1;
+        kern_slab<<<gb, TXE * NB, S::total, c->stream>>>(B, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]);
         SVL_CHECK(cudaGetLastError());
         TileArgs I = A;
         I.wait_flags = nullptr; memset(&I.push, 0, sizeof(I.push)); I.trace = nullptr;
         I.row0 = nlo; I.nrow = nty_ - nlo - nhi;
-        int ni = ntx_ * I.nrow;
+        int gi = c->opt_slab_bnd < 0 ? slots : slots - gb;
+        if (gi < 1) gi = 1;
+        if (gi > ni) gi = ni;
         cudaLaunchConfig_t lc;
         memset(&lc, 0, sizeof(lc));
-        lc.gridDim = dim3(ni < slots ? ni : slots); lc.blockDim = dim3(TXE * NB); lc.dynamicSmemBytes = S::total; lc.stream = c->stream;
+        lc.gridDim = dim3(gi); lc.blockDim = dim3(TXE * NB); lc.dynamicSmemBytes = S::total; lc.stream = c->stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
