@@ -92,6 +92,29 @@ __device__ __forceinline__ void link_sincos<float, 1>(float x, float *s, float *
     asm("sin.approx.ftz.f32 %0, %1;" : "=f"(*s) : "f"(r));
     asm("cos.approx.ftz.f32 %0, %1;" : "=f"(*c) : "f"(r));
 }
+// The two links of a node together: both polynomial cores run unconditionally and side by side (their constants are
+// fetched once, the two Horner chains interleave) and ONE rarely taken test covers both arguments.
+template <typename R, int LINKS>
+__device__ __forceinline__ void link_sincos2(R xa, R xb, R *sa, R *ca, R *sb, R *cb) {
+    sincos_fast(xa, sa, ca);
+    sincos_fast(xb, sb, cb);
+    if (!(sincos_fast_ok(xa) && sincos_fast_ok(xb))) { sincos_any(xa, sa, ca); sincos_any(xb, sb, cb); }
+}
+template <>
+__device__ __forceinline__ void link_sincos2<float, 1>(float xa, float xb, float *sa, float *ca, float *sb, float *cb) {
+    link_sincos<float, 1>(xa, sa, ca);
+    link_sincos<float, 1>(xb, sb, cb);
+}
+// 1/D of the Jacobi diagonal (D of order 1, never denormal): hardware seed + Newton steps, <= 1 ulp, no slow path
+__device__ __forceinline__ float rcp_diag(float x) { return rcp_r(x); }
+__device__ __forceinline__ double rcp_diag(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));         // MUFU.RCP64H: ~20 bits
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    const double e = fma(-x, r, 1.0);                              // third step: the residual of a 40+ bit estimate
+    return fma(r, e, r);
+}
 
 template <typename R, int K, int TXE, int V, int NB, bool EPS, bool SLAB, int LINKS>
 __global__ void __launch_bounds__(TXE *NB, (sizeof(R) == 4 ? 2 : 1))
@@ -269,15 +292,16 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
                 const double2 w0 = *(const double2 *)&s_fl[f][0], w1 = *(const double2 *)&s_fl[f][2];
                 wE = w0.x; wN = w0.y; nw = w1.x; act = w1.y;
             }
-            R sn, cs;
+            R sa, ca, sb, cb;
             C la, lb;
-            link_sincos<R, LINKS>(dx * av, &sn, &cs); la.x = wE * cs; la.y = wE * sn;
-            link_sincos<R, LINKS>(dy * bv, &sn, &cs); lb.x = wN * cs; lb.y = wN * sn;
+            link_sincos2<R, LINKS>(dx * av, dy * bv, &sa, &ca, &sb, &cb);
+            la.x = wE * ca; la.y = wE * sa;
+            lb.x = wN * cb; lb.y = wN * sb;
             qq.x *= act; qq.y *= act;
             const R D = (R)1.0 + dt * (qq.x * qq.x + qq.y * qq.y - e + nw);
             // inactive / out-of-domain nodes stay exactly 0 (td.h:117 writes psi_next = 0): D may vanish there
             // (dt*eps == 1), and 0 * inf would seed NaNs that the zero-weight links then spread
-            const R d = f ? rcp_r(D) : (R)0;
+            const R d = f ? rcp_diag(D) : (R)0;
             psi[v] = p0; q[v] = qq; La[v] = la; Lb[v] = lb; di[v] = d;
             const int xi = (r + 1) * XW + col + 1;
             xb0[xi] = p0;
@@ -628,12 +652,20 @@ int svl_launch_psi_tile(svl_ctx *c, int K, double dt, double eps, const svl_buf 
     }
     TileIO io = {psi->p[0], rhs->p[0], ab->p[0], ab->p[1], epsf ? epsf->p[0] : nullptr, c->nf};
     if (c->rsize == 4) {
-        if (c->opt_psi_links) {
-            if (epsf) return launch_tile_k<float, 64, 8, 4, true, 1>(c, K, A, io);
-            return launch_tile_k<float, 64, 8, 4, false, 1>(c, K, A, io);
+        // fp32 thread shape (option psi_shape): 0 = 512 threads x 4 rows each at 64 registers, two CTAs = 32 warps per
+        // SM; 1 = 256 threads x 8 rows each at 128 registers, 16 warps per SM (fewer instructions per node, half the
+        // warps to hide latencies and barriers with)
+        const int lk = c->opt_psi_links ? 1 : 0, sh = c->opt_psi_shape ? 1 : 0, ep = epsf ? 1 : 0;
+        switch (sh * 4 + lk * 2 + ep) {
+            case 0: return launch_tile_k<float, 64, 4, 8, false, 0>(c, K, A, io);
+            case 1: return launch_tile_k<float, 64, 4, 8, true, 0>(c, K, A, io);
+            case 2: return launch_tile_k<float, 64, 4, 8, false, 1>(c, K, A, io);
+            case 3: return launch_tile_k<float, 64, 4, 8, true, 1>(c, K, A, io);
+            case 4: return launch_tile_k<float, 64, 8, 4, false, 0>(c, K, A, io);
+            case 5: return launch_tile_k<float, 64, 8, 4, true, 0>(c, K, A, io);
+            case 6: return launch_tile_k<float, 64, 8, 4, false, 1>(c, K, A, io);
+            default: return launch_tile_k<float, 64, 8, 4, true, 1>(c, K, A, io);
         }
-        if (epsf) return launch_tile_k<float, 64, 8, 4, true, 0>(c, K, A, io);
-        return launch_tile_k<float, 64, 8, 4, false, 0>(c, K, A, io);
     }
     if (epsf) return launch_tile_k<double, 64, 4, 8, true, 0>(c, K, A, io);
     return launch_tile_k<double, 64, 4, 8, false, 0>(c, K, A, io);
