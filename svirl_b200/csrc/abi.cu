@@ -92,8 +92,12 @@ extern "C" int svl_create(svl_ctx **out, int device_id, int Nx, int Ny, double d
     SVL_CHECK(cudaMalloc(&c->nf, nfb));
     SVL_CHECK(cudaMalloc(&c->d_result, 64 * sizeof(double)));
     SVL_CHECK(cudaMallocHost(&c->h_result, 64 * sizeof(double)));
-    SVL_CHECK(cudaMalloc(&c->d_resid, SVL_MAX_SWEEPS * sizeof(unsigned long long)));
-    SVL_CHECK(cudaMallocHost(&c->h_resid, SVL_MAX_SWEEPS * sizeof(unsigned long long)));
+    SVL_CHECK(cudaMalloc(&c->d_resid_base, 2 * SVL_MAX_SWEEPS * sizeof(unsigned long long)));
+    SVL_CHECK(cudaMallocHost(&c->h_resid_base, 2 * SVL_MAX_SWEEPS * sizeof(unsigned long long)));
+    c->d_resid = c->d_resid_base; c->h_resid = c->h_resid_base; c->resid_bank = 0;
+    SVL_CHECK(cudaMalloc(&c->d_go, sizeof(int)));
+    SVL_CHECK(cudaMemsetAsync(c->d_go, 0, sizeof(int), c->stream));
+    c->opt_pipeline = 1;
     SVL_CHECK(cudaMalloc(&c->d_counter, 16 * sizeof(unsigned int)));
     SVL_CHECK(cudaMemsetAsync(c->d_counter, 0, 16 * sizeof(unsigned int), c->stream));
     SVL_CHECK(cudaMalloc(&c->d_ncand, sizeof(unsigned long long)));
@@ -143,7 +147,7 @@ extern "C" int svl_destroy(svl_ctx *c) {
     cudaFree(c->arena);
     cudaFree(c->board);
     cudaFree(c->nf); cudaFree(c->d_result); cudaFreeHost(c->h_result);
-    cudaFree(c->d_resid); cudaFreeHost(c->h_resid); cudaFree(c->d_counter);
+    cudaFree(c->d_resid_base); cudaFreeHost(c->h_resid_base); cudaFree(c->d_counter); cudaFree(c->d_go);
     cudaFree(c->partials); cudaFree(c->d_cand); cudaFree(c->d_candv); cudaFree(c->d_ncand);
     for (int k = 0; k < 8; k++) cudaEventDestroy(c->ev[k]);
     cudaFreeHost(c->h_err);
@@ -191,6 +195,7 @@ extern "C" int svl_set_option(svl_ctx *c, const char *name, int v) {
     if (!strcmp(name, "psi_kernel")) c->opt_psi_kernel = v;
     else if (!strcmp(name, "psi_k")) { SVL_REQUIRE(v >= 1 && v <= SVL_HALO, "psi_k out of range"); c->opt_psi_k = v; }
     else if (!strcmp(name, "psi_links")) c->opt_psi_links = v;         // fp32 tile kernel: 1 = link variables by MUFU sin/cos (psi_tile.cu)
+    else if (!strcmp(name, "pipeline")) c->opt_pipeline = v;           // kappa = inf time stepping: pre-issue the next step's first launch behind a device-side gate (td.cu)
     else if (!strcmp(name, "psi_shape")) c->opt_psi_shape = v;         // fp32 tile kernel: 0 = 512 threads x 4 rows, 1 = 256 threads x 8 rows
     else if (!strcmp(name, "tma")) c->opt_tma = v;
     else if (!strcmp(name, "graphs")) c->opt_graphs = v;
@@ -224,6 +229,8 @@ extern "C" int svl_get_stat(svl_ctx *c, const char *name, double *v) {
     else if (!strcmp(name, "cg_fused")) *v = c->opt_cg_fused;
     else if (!strcmp(name, "slab_on")) *v = c->slab_on;
     else if (!strcmp(name, "replays")) *v = c->stat_replays;
+    else if (!strcmp(name, "spec_hit")) *v = c->stat_spec_hit;
+    else if (!strcmp(name, "spec_miss")) *v = c->stat_spec_miss;
     else if (!strcmp(name, "psi_sweeps")) *v = c->stat_psi_sweeps;
     else if (!strcmp(name, "A_sweeps")) *v = c->stat_A_sweeps;
     else if (!strcmp(name, "pitch")) *v = c->g.P;

@@ -130,6 +130,14 @@ struct svl_ctx {
     long long spin_limit;          // clock64 cycles, 0 = unbounded
     int *h_err, *d_err;
     void *tma_cache;               // tensor-map descriptors of this context's planes (psi_tile.cu)
+    // pipelined psi solves (td.cu): two banks of residual slots, the device-side go word of a pre-issued launch
+    unsigned long long *d_resid_base, *h_resid_base;   // 2 x SVL_MAX_SWEEPS each; d_resid / h_resid point at the current bank
+    int resid_bank;
+    int *d_go;                     // written by k_psi_gate, read by the pre-issued tile launch
+    const int *spec_gate;          // non-null while a gated launch is being issued (svl_launch_psi_tile picks it up)
+    int spec_issued, spec_K;       // the next psi solve's first launch (spec_K sweeps) is already in the stream
+    int opt_pipeline;              // option "pipeline" (default 1)
+    double stat_spec_hit, stat_spec_miss;
     void *ipc_base[2];             // neighbours' arenas as mapped by cudaIpcOpenMemHandle (closed by svl_destroy)
 };
 

@@ -34,6 +34,7 @@ struct TileArgs {
     int row0, nrow, row1, nrow1;   // tile rows this launch covers: [row0, row0+nrow) then [row1, row1+nrow1)
     int permute;                   // slabs, single launch: process the first / last tile row last
     int pdl_trigger;               // slabs, boundary launch: release the programmatic dependent (interior) launch at once
+    const int *gate;               // pre-issued launch (td.cu, pipelined solves): do nothing unless *gate != 0
     int defer_publish;             // slabs, boundary launch: a CTA fences and reports its pushed tiles ONCE, after its last tile
     SpinGuard sg;                  // bound of the spin waits (halo flags, TMA barrier)
     unsigned long long *trace;     // slabs, diagnostics: [0] first CTA start, [1] last CTA end, [2] longest flag wait,
@@ -132,6 +133,8 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
     C *sla = (C *)(smem + S::off_la);
     uint64_t *bar = (uint64_t *)(smem + S::off_bar);
 
+    // A launch issued ahead of the host's decision runs only if the device-side stop rule agreed (td.cu: k_psi_gate)
+    if (A.gate && *(const volatile int *)A.gate == 0) return;
     const Geo &g = A.g;
     const int tid = threadIdx.x;
     const int col = tid % TXE, band = tid / TXE;
@@ -641,6 +644,7 @@ int svl_launch_psi_tile(svl_ctx *c, int K, double dt, double eps, const svl_buf 
     A.same_rhs = rhs->p[0] == psi->p[0];
     A.out = out->p[0]; A.slots = resid_slots;
     A.sg = svl_spin_guard(c);
+    A.gate = c->spec_gate;
     if (c->slab_on && !c->opt_slab_nocomm) {
         A.wait_flags = c->flags; A.wait_epoch = svl_slab_epoch(c); A.has_lo = c->has_lo; A.has_hi = c->has_hi;
         svl_slab_mark_waited(c);

@@ -216,23 +216,56 @@ static bool stop_rule(const svl_ctx *c, double r, double eps) {
     return (int)v < 10000;
 }
 
+// The same decision on the device (pipelined solves): go <- "the first sweep that meets the stop rule is sweep done-1",
+// i.e. the batch that was just launched ends exactly where the reference stops.  IEEE double / float arithmetic as on
+// the host, so both sides always agree.
+__global__ void k_psi_gate(const unsigned long long *slots, int done, double eps, int f32, int *go) {
+    int bad = 0;
+    for (int s = threadIdx.x; s < done; s += 32) {
+        const double r = __longlong_as_double((long long)slots[s]);
+        double v;
+        if (f32) v = (double)(float)(1.0e4 * r / (double)(float)eps);
+        else v = 1.0e4 * r / eps;
+        if (v > 1.0e8) v = 1.0e8;
+        const bool stop = (int)v < 10000;
+        if (stop != (s == done - 1)) bad = 1;
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (threadIdx.x == 0) *go = bad ? 0 : 1;
+}
+
 static inline double slot_value(unsigned long long bits) {
     double d;
     memcpy(&d, &bits, sizeof(d));
     return d;
 }
 
-static int read_resid(svl_ctx *c, int first, int count) {
+// Residual slots [first, first+count) -> host, in two halves so that work can be enqueued between them: the device
+// part (MAX over ranks, copy, event) and the host part (wait for the EVENT, not for the whole stream).
+static bool resid_board(const svl_ctx *c) { return c->board_world > 1 && c->opt_resid_board && !c->opt_slab_nocomm; }
+static int read_resid_enqueue(svl_ctx *c, int first, int count) {
     // slabs: MAX over ranks (bit patterns of non-negative doubles order like integers; exact)
-    const bool board = c->board_world > 1 && c->opt_resid_board && !c->opt_slab_nocomm;
-    if (board) SVL_TRY(svl_board_allmax(c, first, count));                    // peer memory, no host, no NCCL
+    if (resid_board(c)) SVL_TRY(svl_board_allmax(c, first, count));                    // peer memory, no host, no NCCL
     else if (c->reduce_max_dev && !c->opt_slab_nocomm) c->reduce_max_dev(c->d_resid + first, count); // NCCL, enqueued on c->stream
     SVL_CHECK(cudaMemcpyAsync(c->h_resid + first, c->d_resid + first, (size_t)count * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, c->stream));
-    SVL_CHECK(cudaStreamSynchronize(c->stream));
-    SVL_TRY(svl_peer_error(c));
-    if (!board && c->reduce_max_u64 && !c->reduce_max_dev) c->reduce_max_u64(c->h_resid + first, count);
+    SVL_CHECK(cudaEventRecord(c->ev_go, c->stream));
     return 0;
+}
+static int read_resid_finish(svl_ctx *c, int first, int count) {
+    SVL_CHECK(cudaEventSynchronize(c->ev_go));
+    SVL_TRY(svl_peer_error(c));
+    if (!resid_board(c) && c->reduce_max_u64 && !c->reduce_max_dev) c->reduce_max_u64(c->h_resid + first, count);
+    return 0;
+}
+static int read_resid(svl_ctx *c, int first, int count) {
+    SVL_TRY(read_resid_enqueue(c, first, count));
+    return read_resid_finish(c, first, count);
+}
+static void resid_flip(svl_ctx *c) {
+    c->resid_bank ^= 1;
+    c->d_resid = c->d_resid_base + (size_t)c->resid_bank * SVL_MAX_SWEEPS;
+    c->h_resid = c->h_resid_base + (size_t)c->resid_bank * SVL_MAX_SWEEPS;
 }
 
 // How many sweeps to launch before the next read-back.
@@ -348,29 +381,92 @@ static int psi_launch_range(svl_ctx *c, const PsiSolveArgs &A, PsiIter &it, int 
     return 0;
 }
 
-extern "C" int svl_td_psi_solve(svl_ctx *c, double dt, double eps, const svl_buf *epsf, const svl_buf *ab,
-                                svl_buf *psi, double lang_c, uint32_t rand_t, double stop_eps, int *sweeps_out) {
-    SVL_REQUIRE(c, "null context");
-    SVL_TRY(check_kinds(psi, ab, epsf));
+// K of the first launch of a solve that will run `upto` sweeps in its first batch (what psi_launch_range picks)
+static int first_launch_K(svl_ctx *c, int upto) {
+    int want = c->opt_psi_k < upto ? c->opt_psi_k : upto;
+    return svl_psi_stream_fit_k(want);
+}
+
+// Pipelined solves (kappa = inf time stepping, option "pipeline").  The host learns the residuals of a batch ~10 us
+// (one GPU) to ~25 us (slabs: rendezvous over the residual board) after the batch ends, and the GPU would idle until the
+// next solve's first launch arrives.  Instead, right behind the batch the stream gets: the residual read-back, a
+// one-warp kernel that evaluates the reference's stop rule on the device (k_psi_gate), and the NEXT solve's first
+// launch, which does nothing unless the gate says that this batch ended exactly at the stop sweep (the common case:
+// sweep counts are predicted from the previous step).  The host takes the same decision from the same numbers; on a
+// miss the pre-issued launch was a no-op and the solve carries on as before (replay / continuation).
+struct PsiNext { int allow; uint32_t rand_t; };
+
+static int psi_solve(svl_ctx *c, double dt, double eps, const svl_buf *epsf, const svl_buf *ab, svl_buf *psi,
+                     double lang_c, uint32_t rand_t, double stop_eps, int *sweeps_out, const PsiNext *next) {
     PsiIter it;
     it.B0 = psi;
     SVL_TRY(svl_scratch_node(c, 0, &it.S[0]));
     SVL_TRY(svl_scratch_node(c, 1, &it.S[1]));
     it.reset();
     PsiSolveArgs A = {dt, eps, epsf, ab, lang_c, rand_t};
-    SVL_CHECK(cudaMemsetAsync(c->d_resid, 0, SVL_MAX_SWEEPS * sizeof(unsigned long long), c->stream));
     int done = 0, nstop = -1;
+    const bool pre = c->spec_issued != 0;            // this solve's first launch is already in the stream
+    if (pre) {
+        resid_flip(c);                               // ... it wrote to the other bank (zeroed before the launch)
+        it.prev = it.B0; it.cur = it.S[0]; it.toggle = 1; it.lastK = c->spec_K;
+        c->spec_issued = 0;
+    } else {
+        SVL_CHECK(cudaMemsetAsync(c->d_resid, 0, SVL_MAX_SWEEPS * sizeof(unsigned long long), c->stream));
+    }
+    const bool can_pipe = next && next->allow && c->opt_pipeline && c->opt_psi_kernel == 2 &&
+                          (!c->slab_on || c->opt_slab_nocomm || resid_board(c));
+    bool hit = false;
     while (nstop < 0) {
         int upto;
         if (done == 0) upto = first_batch(c->pred_psi, c->pred_psi2);
         else upto = done + more_sweeps(done >= 2 ? slot_value(c->h_resid[done - 2]) : 0.0, slot_value(c->h_resid[done - 1]), stop_eps);
         if (upto > SVL_MAX_SWEEPS) upto = SVL_MAX_SWEEPS;
-        SVL_TRY(psi_launch_range(c, A, it, done, upto, c->opt_psi_kernel == 0));
-        SVL_TRY(read_resid(c, done, upto - done));
+        int from = done;
+        if (done == 0 && pre) {                      // sweeps [0, spec_K) are in flight; the batch size is the one
+            from = it.lastK;                         // the issuer assumed (same prediction inputs)
+            if (upto < from) upto = from;
+        }
+        SVL_TRY(psi_launch_range(c, A, it, from, upto, c->opt_psi_kernel == 0));
+        SVL_TRY(read_resid_enqueue(c, done, upto - done));
+        // ---- pre-issue the next solve's first launch behind the gate
+        bool spec = false;
+        unsigned long long save_epoch = c->epoch_psi, save_waited = c->waited;
+        int specK = 0;
+        if (can_pipe && upto < SVL_MAX_SWEEPS) {
+            k_psi_gate<<<1, 32, 0, c->stream>>>(c->d_resid, upto, stop_eps, c->rsize == 4 ? 1 : 0, c->d_go);
+            SVL_CHECK(cudaGetLastError());
+            // if the gate opens, this solve ends with res = it.cur, nstop = upto: the state the next solve starts from
+            SVL_TRY(svl_swap(c, psi, it.cur));
+            specK = first_launch_K(c, first_batch(upto, c->pred_psi));
+            resid_flip(c);
+            SVL_CHECK(cudaMemsetAsync(c->d_resid, 0, SVL_MAX_SWEEPS * sizeof(unsigned long long), c->stream));
+            c->spec_gate = c->d_go;
+            int rc = svl_launch_psi_tile(c, specK, dt, eps, epsf, ab, psi, psi, it.S[0], lang_c, next->rand_t, c->d_resid);
+            c->spec_gate = nullptr;
+            resid_flip(c);
+            if (rc) { svl_swap(c, psi, it.cur); return rc; }
+            spec = true;
+        }
+        SVL_TRY(read_resid_finish(c, done, upto - done));
         for (int s = done; s < upto; s++)
             if (stop_rule(c, slot_value(c->h_resid[s]), stop_eps)) { nstop = s + 1; break; }
         done = upto;
+        if (spec) {
+            if (nstop == done) { hit = true; c->spec_issued = 1; c->spec_K = specK; c->stat_spec_hit += 1; }
+            else {                                   // the gate stayed shut: undo the host-side bookkeeping of the no-op
+                SVL_TRY(svl_swap(c, psi, it.cur));
+                c->epoch_psi = save_epoch; c->waited = save_waited;
+                c->stat_spec_miss += 1;
+            }
+        }
         if (nstop < 0 && done >= SVL_MAX_SWEEPS) nstop = SVL_MAX_SWEEPS;   // reference: loop exhausts, keeps last iterate
+    }
+    if (hit) {                                       // psi already holds the result; the next solve is under way
+        c->pred_psi2 = c->pred_psi;
+        c->pred_psi = nstop;
+        c->stat_psi_sweeps += nstop;
+        if (sweeps_out) *sweeps_out = nstop;
+        return 0;
     }
     // `done` sweeps were executed; the reference stops after nstop <= done sweeps
     svl_buf *res = it.cur;
@@ -398,6 +494,13 @@ extern "C" int svl_td_psi_solve(svl_ctx *c, double dt, double eps, const svl_buf
     c->stat_psi_sweeps += nstop;
     if (sweeps_out) *sweeps_out = nstop;
     return 0;
+}
+
+extern "C" int svl_td_psi_solve(svl_ctx *c, double dt, double eps, const svl_buf *epsf, const svl_buf *ab,
+                                svl_buf *psi, double lang_c, uint32_t rand_t, double stop_eps, int *sweeps_out) {
+    SVL_REQUIRE(c, "null context");
+    SVL_TRY(check_kinds(psi, ab, epsf));
+    return psi_solve(c, dt, eps, epsf, ab, psi, lang_c, rand_t, stop_eps, sweeps_out, nullptr);
 }
 
 // ----------------------------------------------------------------------------- A solve
@@ -542,9 +645,12 @@ extern "C" int svl_td_run(svl_ctx *c, int Nt, double dt, int solveA, double eps,
                                  stop_A, sweeps, &handled));
         if (handled) return 0;
     }
+    SVL_TRY(check_kinds(psi, ab, epsf));
+    c->spec_issued = 0;
     for (int t = 0; t < Nt; t++) {
         int n = 0;
-        SVL_TRY(svl_td_psi_solve(c, dt, eps, epsf, ab, psi, lang_psi, *rand_t, stop_psi, &n));
+        PsiNext next = {(!solveA && t + 1 < Nt) ? 1 : 0, *rand_t + 1u};
+        SVL_TRY(psi_solve(c, dt, eps, epsf, ab, psi, lang_psi, *rand_t, stop_psi, &n, &next));
         *rand_t += 1u;                       // td.py:204
         if (sweeps) sweeps[0] += n;
         if (solveA) {

@@ -194,3 +194,28 @@ def test_host_step_pipeline_equals_sequential_steps():
         assert np.array_equal(last, want[k]), k
         assert np.array_equal(g.flatten_array(g.vars.order_parameter), want[k]), k
         g.par.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_pipelined_solves_equal_plain_solves_bitwise(dtype):
+    """kappa = inf time stepping with the next step's first launch pre-issued behind the device-side stop rule
+    (option pipeline, svirl_b200/csrc/td.cu) gives the same psi bit for bit and the same sweep counts as the plain
+    driver, with and without Langevin noise; the gate must open at least once for the test to mean anything."""
+    from svirl_b200 import GLSolver
+    Nx, Ny = 300, 270
+    mt = np.ones((Nx - 1, Ny - 1), dtype=bool)
+    mt[100:140, 60:90] = False
+    out = {}
+    for lang in (0.0, 0.05):
+        for pipe in (0, 1):
+            gl = GLSolver(Nx=Nx, Ny=Ny, dx=0.5, dy=0.5, dtype=dtype, gl_parameter=np.inf, homogeneous_external_field=0.1,
+                          random_seed=7, material_tiling=mt, order_parameter_Langevin_coefficient=lang)
+            gl.par.set_option("pipeline", pipe)
+            gl.solve.td(dt=0.1, Nt=6)
+            gl.solve.td(dt=0.1, Nt=30)
+            out[pipe] = (gl.flatten_array(gl.vars.order_parameter).copy(), gl.solve._td.sweeps_order_parameter,
+                         gl.par.stat("spec_hit"), gl.par.stat("spec_miss"))
+            gl.par.close()
+        assert out[0][1] == out[1][1], (lang, out[0][1], out[1][1])
+        assert np.array_equal(out[0][0], out[1][0]), lang
+        assert out[0][2] == 0 and out[1][2] > 0, (lang, out[0][2:], out[1][2:])
