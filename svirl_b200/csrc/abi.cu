@@ -98,6 +98,7 @@ extern "C" int svl_create(svl_ctx **out, int device_id, int Nx, int Ny, double d
     SVL_CHECK(cudaMalloc(&c->d_go, sizeof(int)));
     SVL_CHECK(cudaMemsetAsync(c->d_go, 0, sizeof(int), c->stream));
     c->opt_pipeline = 1;
+    c->opt_pdl = 1;
     SVL_CHECK(cudaMalloc(&c->d_counter, 16 * sizeof(unsigned int)));
     SVL_CHECK(cudaMemsetAsync(c->d_counter, 0, 16 * sizeof(unsigned int), c->stream));
     SVL_CHECK(cudaMalloc(&c->d_ncand, sizeof(unsigned long long)));
@@ -195,6 +196,7 @@ extern "C" int svl_set_option(svl_ctx *c, const char *name, int v) {
     if (!strcmp(name, "psi_kernel")) c->opt_psi_kernel = v;
     else if (!strcmp(name, "psi_k")) { SVL_REQUIRE(v >= 1 && v <= SVL_HALO, "psi_k out of range"); c->opt_psi_k = v; }
     else if (!strcmp(name, "psi_links")) c->opt_psi_links = v;         // fp32 tile kernel: 1 = link variables by MUFU sin/cos (psi_tile.cu)
+    else if (!strcmp(name, "pdl")) c->opt_pdl = v;
     else if (!strcmp(name, "pipeline")) c->opt_pipeline = v;           // kappa = inf time stepping: pre-issue the next step's first launch behind a device-side gate (td.cu)
     else if (!strcmp(name, "psi_shape")) c->opt_psi_shape = v;         // fp32 tile kernel: 0 = 512 threads x 4 rows, 1 = 256 threads x 8 rows
     else if (!strcmp(name, "tma")) c->opt_tma = v;

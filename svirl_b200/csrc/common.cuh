@@ -137,6 +137,7 @@ struct svl_ctx {
     const int *spec_gate;          // non-null while a gated launch is being issued (svl_launch_psi_tile picks it up)
     int spec_issued, spec_K;       // the next psi solve's first launch (spec_K sweeps) is already in the stream
     int opt_pipeline;              // option "pipeline" (default 1)
+    int opt_pdl;                   // option "pdl" (default 1): batches of one solve as programmatic dependent launches
     double stat_spec_hit, stat_spec_miss;
     void *ipc_base[2];             // neighbours' arenas as mapped by cudaIpcOpenMemHandle (closed by svl_destroy)
 };

@@ -33,7 +33,9 @@ struct TileArgs {
     int push_expect[2];            // tiles that contribute to the lo / hi push
     int row0, nrow, row1, nrow1;   // tile rows this launch covers: [row0, row0+nrow) then [row1, row1+nrow1)
     int permute;                   // slabs, single launch: process the first / last tile row last
-    int pdl_trigger;               // slabs, boundary launch: release the programmatic dependent (interior) launch at once
+    int pdl_trigger;               // release a programmatic dependent launch at once (slab boundary launch -> interior launch;
+                                   // one GPU: batch n -> batch n+1, whose CTAs then start up in this launch's tail)
+    int pdl_wait;                  // this launch may have started before its predecessor ended: wait before the first load
     const int *gate;               // pre-issued launch (td.cu, pipelined solves): do nothing unless *gate != 0
     int defer_publish;             // slabs, boundary launch: a CTA fences and reports its pushed tiles ONCE, after its last tile
     SpinGuard sg;                  // bound of the spin waits (halo flags, TMA barrier)
@@ -187,12 +189,14 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
     };
 
     int tile = blockIdx.x;
-    if (SLAB && A.pdl_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (A.pdl_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (SLAB && A.trace && tid == 0) atomicMin(A.trace + 0, gtime());
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(t_smem_u32(bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // everything this launch reads or overwrites comes after its first TMA load, which waits for the predecessor
+        if (A.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
         if (tile < ntiles) issue(tile);
     }
     // zero the pad ring of the exchange / coefficient tiles once (never overwritten afterwards)
@@ -564,7 +568,24 @@ static int launch_tile_t(svl_ctx *c, TileArgs &A, const TileIO &io) {
     A.row0 = 0; A.nrow = nty_; A.row1 = 0; A.nrow1 = 0; A.permute = 0;
     if (!A.wait_flags) {
         int ntiles = ntx_ * nty_;
-        kern<<<ntiles < slots ? ntiles : slots, TXE * NB, S::total, c->stream>>>(A, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]);
+        if (c->opt_pdl && !A.gate) {
+            // Consecutive batches of a solve as programmatic dependent launches: a batch releases its successor at its
+            // first instruction, the successor's CTAs become resident as this batch's CTAs retire, set up their shared
+            // memory and then wait (griddepcontrol.wait, thread 0, before the first TMA load) for this batch to end: the
+            // launch latency, the prologue and part of the tail of every batch are hidden.
+            A.pdl_trigger = 1; A.pdl_wait = 1;
+            cudaLaunchConfig_t lc;
+            memset(&lc, 0, sizeof(lc));
+            lc.gridDim = dim3(ntiles < slots ? ntiles : slots); lc.blockDim = dim3(TXE * NB); lc.dynamicSmemBytes = S::total;
+            lc.stream = c->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            lc.attrs = at; lc.numAttrs = 1;
+            SVL_CHECK(cudaLaunchKernelEx(&lc, kern, A, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]));
+        } else {
+            kern<<<ntiles < slots ? ntiles : slots, TXE * NB, S::total, c->stream>>>(A, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]);
+        }
     } else if (c->opt_slab_split && nty_ - nlo - nhi > 0 && nlo + nhi > 0) {
         // Slabs, two launches per batch ON ONE STREAM: first the boundary tile rows (halo wait + in-kernel push; at
         // most a few dozen CTAs, resident at once), then the interior rows with the plain kernel as a PROGRAMMATIC
