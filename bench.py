@@ -120,6 +120,7 @@ class ClockSampler(object):
 
     def __init__(self, index):
         self.index, self.samples, self.stop_flag, self.th = index, [], False, None
+        self.armed = False
         self.nvml = None
         try:
             import pynvml
@@ -136,27 +137,35 @@ class ClockSampler(object):
         except Exception:
             self.nvml = None
 
-    def _run_nvml(self):
+    def _sample_nvml(self):
         n = self.nvml
         R = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
-        try:
-            mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
-        except Exception:
-            mx = None
-        while not self.stop_flag:
+        if not hasattr(self, "_mx"):
             try:
-                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
-                try:
-                    bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
-                except Exception:
-                    bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-                self.samples.append([sm, mx, [k for k, v in R.items() if bits & v]])
+                self._mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
             except Exception:
-                pass
-            time.sleep(0.002)
+                self._mx = None
+        try:
+            sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            try:
+                bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            self.samples.append([sm, self._mx, [k for k, v in R.items() if bits & v]])
+        except Exception:
+            pass
+
+    def _run_nvml(self):
+        while not self.stop_flag:
+            if self.armed:
+                self._sample_nvml()
+            time.sleep(0.001)
 
     def _run_smi(self):
         while not self.stop_flag:
+            if not self.armed:
+                time.sleep(0.001)
+                continue
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
@@ -168,11 +177,27 @@ class ClockSampler(object):
                 pass
             time.sleep(0.05)
 
-    def start(self):
+    def prepare(self):
+        """Everything slow (NVML first calls, thread start) BEFORE the barrier that precedes the timed region: done after
+        it, it would skew the ranks' start times by milliseconds, which the first timed step then absorbs."""
+        if self.th is not None:
+            return
+        if self.nvml:
+            self._sample_nvml()
+            self.samples = []
         self.th = threading.Thread(target=self._run_nvml if self.nvml else self._run_smi, daemon=True)
         self.th.start()
 
+    def start(self):
+        self.prepare()
+        self.armed = True
+
     def stop(self):
+        """Called right after the last timed step was enqueued and BEFORE the closing synchronize: a short timed region
+        (a few ms) may end before the sampling thread got a turn, so one sample is taken here, with the GPU still busy."""
+        if self.nvml and not self.samples:
+            self._sample_nvml()
+        self.armed = False
         self.stop_flag = True
         if self.th:
             self.th.join(timeout=10)
@@ -181,6 +206,19 @@ class ClockSampler(object):
         reasons = sorted({r for s in self.samples for r in s[2]})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": reasons,
                 "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
+
+
+def aligned_start(world):
+    """After the barrier: all ranks of the box leave at the same instant of the shared monotonic clock (rank 0 names it).
+    A NCCL barrier releases the ranks up to a few hundred microseconds apart; on row slabs every rank waits for its
+    neighbours, so that skew would be charged to the first timed step (it is 5 % of a 20-step cfg2 region)."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    box = [time.clock_gettime(time.CLOCK_MONOTONIC) + 0.005]
+    dist.broadcast_object_list(box, src=0)
+    while time.clock_gettime(time.CLOCK_MONOTONIC) < box[0]:
+        pass
 
 
 # ------------------------------------------------------------------------------------ CPU reference arm
@@ -537,10 +575,12 @@ def measure_scale(wl, rank, world, local, steps, warmup, opts=()):
         torch.cuda.synchronize()
 
     st.td(0.1, max(warmup, 3))
+    sampler = ClockSampler(local)
+    sampler.prepare()
     barrier()
+    aligned_start(world)
     s0 = (st.sweeps[0], st.sweeps[1])
     l0 = st.stat("launches")
-    sampler = ClockSampler(local)
     sampler.start()
     t0 = time.perf_counter()
     _lib.call("svl_event_record", st._ctx, 0)
@@ -699,10 +739,12 @@ def main():
     # ---- warm-up (also settles the sweep-count prediction), then K timed steps
     gl.solve.td(Nt=args.warmup, **td_kw)
     td = gl.solve._td
+    sampler = ClockSampler(local)
+    sampler.prepare()
     barrier()
+    aligned_start(world)
     s0 = (td.sweeps_order_parameter, td.sweeps_vector_potential)
     l0 = par.stat("launches")
-    sampler = ClockSampler(local)
     sampler.start()
     _lib.call("svl_event_record", par.ctx, 0)
     gl.solve.td(Nt=args.steps, **td_kw)
