@@ -156,9 +156,18 @@ class ClockSampler(object):
             pass
 
     def _run_nvml(self):
+        # An NVML query holds a driver lock for ~1 ms, and a launch-bound timed region feels it (measured: one query per
+        # millisecond turned 0.41 ms/step into 1.7).  So: first query 20 ms into the region, then one every 25 ms; a region
+        # shorter than that gets its one sample from stop(), taken the moment the last timed step has finished.
+        t_arm = None
         while not self.stop_flag:
             if self.armed:
-                self._sample_nvml()
+                now = time.perf_counter()
+                if t_arm is None:
+                    t_arm = now + 0.020
+                if now >= t_arm:
+                    self._sample_nvml()
+                    t_arm = time.perf_counter() + 0.025
             time.sleep(0.001)
 
     def _run_smi(self):
@@ -193,11 +202,11 @@ class ClockSampler(object):
         self.armed = True
 
     def stop(self):
-        """Called right after the last timed step was enqueued and BEFORE the closing synchronize: a short timed region
-        (a few ms) may end before the sampling thread got a turn, so one sample is taken here, with the GPU still busy."""
+        """Call it the moment the timed steps have finished (before the closing barrier): a region of a few ms gets its
+        clock sample here -- SM clocks do not drop within microseconds of the last kernel -- see _run_nvml."""
+        self.armed = False
         if self.nvml and not self.samples:
             self._sample_nvml()
-        self.armed = False
         self.stop_flag = True
         if self.th:
             self.th.join(timeout=10)
@@ -211,14 +220,25 @@ class ClockSampler(object):
 def aligned_start(world):
     """After the barrier: all ranks of the box leave at the same instant of the shared monotonic clock (rank 0 names it).
     A NCCL barrier releases the ranks up to a few hundred microseconds apart; on row slabs every rank waits for its
-    neighbours, so that skew would be charged to the first timed step (it is 5 % of a 20-step cfg2 region)."""
+    neighbours, so that skew would be charged to the first timed step (it is 5 % of a 20-step cfg2 region).  The instant
+    is agreed on with two small collectives; a rank that hears of it too late makes everybody try again with more margin."""
     if world <= 1:
         return
+    import torch
     import torch.distributed as dist
-    box = [time.clock_gettime(time.CLOCK_MONOTONIC) + 0.005]
-    dist.broadcast_object_list(box, src=0)
-    while time.clock_gettime(time.CLOCK_MONOTONIC) < box[0]:
-        pass
+    clock = lambda: time.clock_gettime(time.CLOCK_MONOTONIC)       # noqa: E731
+    t = torch.zeros(1, dtype=torch.float64, device="cuda")
+    for margin in (0.01, 0.05, 0.25):
+        if dist.get_rank() == 0:
+            t[0] = clock() + margin
+        dist.broadcast(t, 0)
+        target = float(t.item())
+        ok = torch.tensor([1.0 if clock() < target - 0.004 else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) > 0.0 and clock() < target:
+            while clock() < target:
+                pass
+            return
 
 
 # ------------------------------------------------------------------------------------ CPU reference arm
@@ -751,8 +771,8 @@ def main():
     _lib.call("svl_event_record", par.ctx, 1)
     ms = C.c_double()
     _lib.call("svl_event_elapsed_ms", par.ctx, 0, 1, C.byref(ms))
-    barrier()
     clocks = sampler.stop()
+    barrier()
     launches = par.stat("launches") - l0
     sw_psi = td.sweeps_order_parameter - s0[0]
     sw_A = td.sweeps_vector_potential - s0[1]
