@@ -400,13 +400,22 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
         const int rows_own = g.j1 - g.j0;
         const bool plo = SLAB && A.push.peer[0][0] && by * TYO < A.push.depth;
         const bool phi = SLAB && A.push.peer[1][0] && ((by + 1) * TYO < rows_own ? (by + 1) * TYO : rows_own) > rows_own - A.push.depth;
+        {
+            // one 64-bit address per thread, then a constant row stride: the stores are predicated, not branched around
+            C *o = (C *)A.out + ((long long)(yg0 + r0 - g.rb) * g.P + x);
 #pragma unroll
-        for (int v = 0; v < V; v++) {
-            if (inmask & (1u << v)) {
-                const int y = yg0 + r0 + v;
-                ((C *)A.out)[g.at(x, y)] = psi[v];
-                if (plo && y < g.j0 + A.push.depth) ((C *)A.push.peer[0][0])[(size_t)(y - A.push.peer_rb[0]) * g.P + x] = psi[v];
-                if (phi && y >= g.j1 - A.push.depth) ((C *)A.push.peer[1][0])[(size_t)(y - A.push.peer_rb[1]) * g.P + x] = psi[v];
+            for (int v = 0; v < V; v++) {
+                if (inmask & (1u << v)) o[(long long)v * g.P] = psi[v];
+            }
+            if (SLAB && (plo || phi)) {
+#pragma unroll
+                for (int v = 0; v < V; v++) {
+                    if (inmask & (1u << v)) {
+                        const int y = yg0 + r0 + v;
+                        if (plo && y < g.j0 + A.push.depth) ((C *)A.push.peer[0][0])[(size_t)(y - A.push.peer_rb[0]) * g.P + x] = psi[v];
+                        if (phi && y >= g.j1 - A.push.depth) ((C *)A.push.peer[1][0])[(size_t)(y - A.push.peer_rb[1]) * g.P + x] = psi[v];
+                    }
+                }
             }
         }
         if (plo || phi) {                        // CTA-uniform
