@@ -554,6 +554,16 @@ def also_blocks(args):
         r["gpu_baseline"] = bref_cg(wl, 3)
         return r
 
+    def cfg4():
+        # BASELINE configs[3] at its full size (16384^2): the kernels take 4x longer than at 8192^2 while the host line
+        # search does not, so this is the CG iteration's roofline fraction at the size the target is quoted on
+        wl = dict(workload("cfg4"), key="cfg4")
+        gl = make_solver(wl)
+        r = measure_cg(wl, gl, gl.par, 6, 2, "reference")
+        gl.par.close()
+        del gl
+        return r
+
     def cfg1():
         wl = workload("cfg1")
         gl = make_solver(wl)
@@ -563,7 +573,7 @@ def also_blocks(args):
         r["gpu_baseline"] = bref_td(wl, 200, 50)
         return r
 
-    for name, fn in (("cfg3", cfg3), ("cfg4s", cfg4s), ("cfg1", cfg1)):
+    for name, fn in (("cfg3", cfg3), ("cfg4s", cfg4s), ("cfg4", cfg4), ("cfg1", cfg1)):
         if name in args.also.split(","):
             guarded(name, fn)
     return out
@@ -674,7 +684,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-instances", type=int, default=3,
                     help="independent solver instances in flight in the end-to-end (host buffer) measurement; 1 = a single one")
-    ap.add_argument("--also", default="cfg3,cfg4s,cfg1", help="extra single-GPU configs reported in `also` (default line only)")
+    ap.add_argument("--also", default="cfg3,cfg4s,cfg4,cfg1", help="extra single-GPU configs reported in `also` (default line only)")
     ap.add_argument("--no-extras", action="store_true", help="main line only: no parity / gpu_baseline / also / strong blocks")
     ap.add_argument("--line-search", default=None, choices=[None, "reference", "normalized", "native"])
     args = ap.parse_args()

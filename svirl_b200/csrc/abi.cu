@@ -98,7 +98,7 @@ extern "C" int svl_create(svl_ctx **out, int device_id, int Nx, int Ny, double d
     SVL_CHECK(cudaMalloc(&c->d_go, sizeof(int)));
     SVL_CHECK(cudaMemsetAsync(c->d_go, 0, sizeof(int), c->stream));
     c->opt_pipeline = 1;
-    c->opt_pdl = 1;
+    { const char *e = getenv("SVL_PDL"); c->opt_pdl = e ? atoi(e) : 2; }   // 0 off, 1 one GPU only, 2 also the launch pairs of slab batches
     SVL_CHECK(cudaMalloc(&c->d_counter, 16 * sizeof(unsigned int)));
     SVL_CHECK(cudaMemsetAsync(c->d_counter, 0, 16 * sizeof(unsigned int), c->stream));
     SVL_CHECK(cudaMalloc(&c->d_ncand, sizeof(unsigned long long)));

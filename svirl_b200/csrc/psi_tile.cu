@@ -36,6 +36,8 @@ struct TileArgs {
     int pdl_trigger;               // release a programmatic dependent launch at once (slab boundary launch -> interior launch;
                                    // one GPU: batch n -> batch n+1, whose CTAs then start up in this launch's tail)
     int pdl_wait;                  // this launch may have started before its predecessor ended: wait before the first load
+                                   // (pdl_trigger == 2: release the dependent launch only after that wait)
+    int pdl_wait_end;              // slabs, interior launch: do not COMPLETE before the boundary launch it ran beside has
     const int *gate;               // pre-issued launch (td.cu, pipelined solves): do nothing unless *gate != 0
     int defer_publish;             // slabs, boundary launch: a CTA fences and reports its pushed tiles ONCE, after its last tile
     SpinGuard sg;                  // bound of the spin waits (halo flags, TMA barrier)
@@ -189,7 +191,7 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
     };
 
     int tile = blockIdx.x;
-    if (A.pdl_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (A.pdl_trigger == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (SLAB && A.trace && tid == 0) atomicMin(A.trace + 0, gtime());
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(t_smem_u32(bar)));
@@ -210,6 +212,10 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
             xb0[i * XW] = z; xb1[i * XW] = z; sla[i * XW] = z;
             xb0[i * XW + XW - 1] = z; xb1[i * XW + XW - 1] = z; sla[i * XW + XW - 1] = z;
         }
+    }
+    if (A.pdl_trigger == 2) {                // chained slab batches: the interior launch may go once the previous batch is over
+        __syncthreads();                     // thread 0 is past its griddepcontrol.wait
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     }
     __shared__ unsigned int sm_rmax[K];      // per-sweep max-norm update of this CTA (bit patterns of floats/doubles >= 0)
     __shared__ unsigned long long sm_rmax64[K];
@@ -456,6 +462,7 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
         }
     }
     if (SLAB && A.trace && tid == 0) atomicMax(A.trace + 1, gtime());
+    if (A.pdl_wait_end && tid == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
     // ---- per-sweep max-norm updates -> one global atomicMax per CTA and sweep
     __syncthreads();
     if (tid < K) {
@@ -620,10 +627,28 @@ static int launch_tile_t(svl_ctx *c, TileArgs &A, const TileIO &io) {
             }
         }
         B.defer_publish = 1;
-        kern_slab<<<gb, TXE * NB, S::total, c->stream>>>(B, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]);
+        const bool chain = c->opt_pdl >= 2 && !A.gate;
+        if (chain) {
+            // Batches chained across the pair of launches: this boundary launch is a programmatic dependent of the previous
+            // batch's INTERIOR launch (which released it at its first instruction and does not complete before its own
+            // boundary launch has, pdl_wait_end); its CTAs set up, wait for that batch to end, and only then release this
+            // batch's interior launch.
+            B.pdl_wait = 1; B.pdl_trigger = 2;
+            cudaLaunchConfig_t lb;
+            memset(&lb, 0, sizeof(lb));
+            lb.gridDim = dim3(gb); lb.blockDim = dim3(TXE * NB); lb.dynamicSmemBytes = S::total; lb.stream = c->stream;
+            cudaLaunchAttribute ab[1];
+            ab[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            ab[0].val.programmaticStreamSerializationAllowed = 1;
+            lb.attrs = ab; lb.numAttrs = 1;
+            SVL_CHECK(cudaLaunchKernelEx(&lb, kern_slab, B, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]));
+        } else {
+            kern_slab<<<gb, TXE * NB, S::total, c->stream>>>(B, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]);
+        }
         SVL_CHECK(cudaGetLastError());
         TileArgs I = A;
         I.wait_flags = nullptr; memset(&I.push, 0, sizeof(I.push)); I.trace = nullptr;
+        if (chain) { I.pdl_trigger = 1; I.pdl_wait_end = 1; }
         I.row0 = nlo; I.nrow = nty_ - nlo - nhi;
         int gi = c->opt_slab_bnd < 0 ? slots : slots - gb;
         if (gi < 1) gi = 1;
@@ -701,6 +726,7 @@ int svl_launch_psi_tile(svl_ctx *c, int K, double dt, double eps, const svl_buf 
             default: return launch_tile_k<float, 64, 8, 4, true, 1>(c, K, A, io);
         }
     }
+    // (fp64 with 256 threads x 8 rows at 244 registers, 8 warps per SM, was measured: cfg3 18.9 -> 19.9 ms/step)
     if (epsf) return launch_tile_k<double, 64, 4, 8, true, 0>(c, K, A, io);
     return launch_tile_k<double, 64, 4, 8, false, 0>(c, K, A, io);
 }
