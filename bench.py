@@ -121,6 +121,7 @@ class ClockSampler(object):
     def __init__(self, index):
         self.index, self.samples, self.stop_flag, self.th = index, [], False, None
         self.armed = False
+        self.wake, self.wake2 = threading.Event(), threading.Event()      # start() / stop()
         self.nvml = None
         try:
             import pynvml
@@ -159,16 +160,17 @@ class ClockSampler(object):
         # An NVML query holds a driver lock for ~1 ms, and a launch-bound timed region feels it (measured: one query per
         # millisecond turned 0.41 ms/step into 1.7).  So: first query 20 ms into the region, then one every 25 ms; a region
         # shorter than that gets its one sample from stop(), taken the moment the last timed step has finished.
-        t_arm = None
+        # The thread sleeps on an Event (no periodic wake-ups while the ranks are being timed: a box has ~2 host threads
+        # per GPU rank).
+        self.wake.wait()
+        if self.stop_flag:
+            return
+        if self.wake2.wait(0.020):
+            return
         while not self.stop_flag:
-            if self.armed:
-                now = time.perf_counter()
-                if t_arm is None:
-                    t_arm = now + 0.020
-                if now >= t_arm:
-                    self._sample_nvml()
-                    t_arm = time.perf_counter() + 0.025
-            time.sleep(0.001)
+            self._sample_nvml()
+            if self.wake2.wait(0.025):
+                return
 
     def _run_smi(self):
         while not self.stop_flag:
@@ -200,14 +202,17 @@ class ClockSampler(object):
     def start(self):
         self.prepare()
         self.armed = True
+        self.wake.set()
 
     def stop(self):
         """Call it the moment the timed steps have finished (before the closing barrier): a region of a few ms gets its
         clock sample here -- SM clocks do not drop within microseconds of the last kernel -- see _run_nvml."""
         self.armed = False
+        self.stop_flag = True
+        self.wake.set()
+        self.wake2.set()
         if self.nvml and not self.samples:
             self._sample_nvml()
-        self.stop_flag = True
         if self.th:
             self.th.join(timeout=10)
         sm = [s[0] for s in self.samples]
