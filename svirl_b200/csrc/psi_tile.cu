@@ -616,15 +616,24 @@ static int launch_tile_t(svl_ctx *c, TileArgs &A, const TileIO &io) {
         const int nb = ntx_ * (nlo + nhi), ni = ntx_ * (nty_ - nlo - nhi);
         // The boundary tiles go to a FEW CTAs (each takes several tiles and fences once), the interior kernel gets the
         // remaining slots, all resident from the start: a boundary CTA holds its slot through the system-scope fence,
-        // and an interior CTA that had to wait for that slot would finish its static share of tiles late.  Smallest
-        // boundary grid whose CTAs (tiles + ~3 tile times of fence) still finish well before the interior does.
+        // and an interior CTA that had to wait for that slot would finish its static share of tiles late.  The batch
+        // lasts max(rounds of the interior CTAs, rounds of the boundary CTAs + ~3 tile times of fence) tile times; both
+        // are step functions of the split (2048^2 per GPU with two neighbours: 13 boundary CTAs keep the interior at
+        // 11 rounds like a single GPU, 15 would push it to 12), so the split is chosen by evaluating that maximum.
         int gb = nb < slots ? nb : slots;
         if (c->opt_slab_bnd > 0) gb = c->opt_slab_bnd < gb ? c->opt_slab_bnd : gb;
         else if (c->opt_slab_bnd == 0) {
-            for (int t = 4; t < gb; t++) {
-                const double tb = (double)((nb + t - 1) / t) + 3.0, ti = (double)ni / (double)(slots - t);
-                if (slots - t > 0 && tb <= 0.8 * ti) { gb = t; break; }
+            long best = -1, best_b = 0;
+            int best_t = gb;
+            const int tmax = nb < slots / 2 ? nb : slots / 2;
+            for (int t = 1; t <= tmax; t++) {
+                const long rb = (nb + t - 1) / t + 3, ri = ((long)ni + (slots - t) - 1) / (slots - t);
+                // the boundary CTAs should be done well before the interior ones: their tiles wait for halo flags and
+                // their fence time is only roughly known
+                const long r = 20 * rb > 17 * ri ? (rb * 20 + 16) / 17 : ri;
+                if (best < 0 || r < best || (r == best && rb < best_b)) { best = r; best_b = rb; best_t = t; }
             }
+            gb = best_t;
         }
         B.defer_publish = 1;
         const bool chain = c->opt_pdl >= 2 && !A.gate;
