@@ -122,7 +122,7 @@ __device__ __forceinline__ double rcp_diag(double x) {
 }
 
 template <typename R, int K, int TXE, int V, int NB, bool EPS, bool SLAB, int LINKS>
-__global__ void __launch_bounds__(TXE *NB, (sizeof(R) == 4 ? 2 : 1))
+__global__ void __launch_bounds__(TXE *NB, ((sizeof(R) == 4 && V * NB <= 32) ? 2 : 1))
 k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorMap tm_psi,
            const __grid_constant__ CUtensorMap tm_rhs, const __grid_constant__ CUtensorMap tm_a,
            const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_eps,
@@ -724,6 +724,9 @@ int svl_launch_psi_tile(svl_ctx *c, int K, double dt, double eps, const svl_buf 
         // SM; 1 = 256 threads x 8 rows each at 128 registers, 16 warps per SM (fewer instructions per node, half the
         // warps to hide latencies and barriers with)
         const int lk = c->opt_psi_links ? 1 : 0, sh = c->opt_psi_shape ? 1 : 0, ep = epsf ? 1 : 0;
+        // (64 x 64 tiles -- 77 % instead of 66 % of the computed nodes are output -- on 512 threads, one CTA per SM, were
+        // measured as well: 9 % fewer instructions, 0.370 vs 0.365 ms/step; one CTA per SM leaves nobody to issue while
+        // its warps sit at the sweep barrier, and 1369 tiles on 148 CTAs quantise worse than 3182 on 296)
         switch (sh * 4 + lk * 2 + ep) {
             case 0: return launch_tile_k<float, 64, 4, 8, false, 0>(c, K, A, io);
             case 1: return launch_tile_k<float, 64, 4, 8, true, 0>(c, K, A, io);
