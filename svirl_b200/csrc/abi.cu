@@ -117,6 +117,7 @@ extern "C" int svl_create(svl_ctx **out, int device_id, int Nx, int Ny, double d
         const char *e = getenv("SVL_PSI_LINKS");
         c->opt_psi_links = e ? atoi(e) : 1;
     }
+    { const char *e = getenv("SVL_PSI_PATCH"); c->opt_psi_patch = e ? atoi(e) : 1; }   // 2 x 4 patch kernel (bit-identical to the column kernel, 3.4 % faster at cfg2)
     c->opt_psi_shape = 1;          // 256 threads x 8 rows (measured 63.2 vs 65.1 us per K=4 launch at 2048^2 for 512 x 4)
     c->opt_tma = 1;
     c->opt_graphs = 1;
@@ -198,6 +199,7 @@ extern "C" int svl_set_option(svl_ctx *c, const char *name, int v) {
     else if (!strcmp(name, "psi_links")) c->opt_psi_links = v;         // fp32 tile kernel: 1 = link variables by MUFU sin/cos (psi_tile.cu)
     else if (!strcmp(name, "pdl")) c->opt_pdl = v;
     else if (!strcmp(name, "pipeline")) c->opt_pipeline = v;           // kappa = inf time stepping: pre-issue the next step's first launch behind a device-side gate (td.cu)
+    else if (!strcmp(name, "psi_patch")) c->opt_psi_patch = v;         // fp32 tile kernel: 1 = 2 x 4 node patch per thread (k_psi_patch), 0 = 1 x 8 column
     else if (!strcmp(name, "psi_shape")) c->opt_psi_shape = v;         // fp32 tile kernel: 0 = 512 threads x 4 rows, 1 = 256 threads x 8 rows
     else if (!strcmp(name, "tma")) c->opt_tma = v;
     else if (!strcmp(name, "graphs")) c->opt_graphs = v;

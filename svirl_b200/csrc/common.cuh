@@ -96,7 +96,7 @@ struct svl_ctx {
     // vortex candidates
     long long *d_cand; double *d_candv; unsigned long long *d_ncand; size_t cand_cap;
     // options / stats
-    int opt_psi_kernel, opt_psi_k, opt_psi_links, opt_psi_shape, opt_tma, opt_graphs, opt_a_kernel, opt_cg_fused, opt_resid_board, opt_slab_nocomm, opt_slab_split, opt_slab_bnd, opt_cg_slabs;
+    int opt_psi_kernel, opt_psi_k, opt_psi_links, opt_psi_shape, opt_psi_patch, opt_tma, opt_graphs, opt_a_kernel, opt_cg_fused, opt_resid_board, opt_slab_nocomm, opt_slab_split, opt_slab_bnd, opt_cg_slabs;
     int pred_psi, pred_A;          // sweep counts of the previous solve
     int pred_psi2, pred_A2;        // ... and of the one before (trend)
     double stat_launches, stat_replays, stat_psi_sweeps, stat_A_sweeps;

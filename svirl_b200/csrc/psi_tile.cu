@@ -471,6 +471,265 @@ k_psi_tile(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorM
     }
 }
 
+// ------------------------------------------------------------------------------- 2 x 4 patch variant (fp32)
+// Same tile, same staging, same arithmetic per node (bit-identical results) as k_psi_tile<float, K, 64, 8, 4>, but a
+// thread owns a PATCH of 2 columns x 4 rows instead of a column of 8 rows: lane l of warp w holds columns 2l, 2l+1 of
+// tile rows 4w .. 4w+3.  The E neighbour of the even column and the W neighbour (and W link coefficient) of the odd
+// column are then the thread's own registers, and the iterate is exchanged through separate planes for the even and the
+// odd columns, so that what a warp reads is contiguous: 16 LDS.64 + 8 STS.64 per sweep and thread instead of 26 + 8
+// (the shared-memory pipe was 55 % busy next to 61 % of the issue slots), LDS.128 / LDS.64 instead of LDS.64 / LDS.32
+// in the constants loop.  Non-slab launches only (one GPU, and the interior launch of a slab batch); the boundary tile
+// rows of a slab keep the column kernel -- every node gets the same bits from either.
+template <int K, bool EPS, int LINKS>
+__global__ void __launch_bounds__(256, 2)
+k_psi_patch(const __grid_constant__ TileArgs A, const __grid_constant__ CUtensorMap tm_psi,
+            const __grid_constant__ CUtensorMap tm_rhs, const __grid_constant__ CUtensorMap tm_a,
+            const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_eps,
+            const __grid_constant__ CUtensorMap tm_nf) {
+    typedef float R;
+    typedef float2 C;
+    typedef TileSmem<float, K, 64, 8, 4, EPS> S;
+    constexpr int TXE = 64, EY = S::EY, H = S::H, NFW = S::NFW, PR = 4, XR = EY + 2, PW = 33;
+    constexpr int TX = TXE - 2 * H, TYO = EY - 2 * K, NT = 256;
+    static_assert(5 * XR * PW * sizeof(C) <= 3 * sizeof(C) * S::XR * S::XW, "patch planes must fit the exchange area");
+    extern __shared__ __align__(128) unsigned char smem[];
+    C *pl = (C *)(smem + S::off_x0);
+    C *xe[2] = {pl, pl + 2 * XR * PW};                 // even columns: column 2l at index l, index 32 = zero pad (column 64)
+    C *xo[2] = {pl + XR * PW, pl + 3 * XR * PW};       // odd columns: column 2l+1 at index l+1, index 0 = zero pad (column -1)
+    C *slo = pl + 4 * XR * PW;                         // E-link coefficient of the odd columns (= W coefficient of the even ones)
+    uint64_t *bar = (uint64_t *)(smem + S::off_bar);
+
+    if (A.gate && *(const volatile int *)A.gate == 0) return;
+    const Geo &g = A.g;
+    const int tid = threadIdx.x, lane = tid & 31, r0 = (tid >> 5) * PR, c0 = 2 * lane;
+    const int ntx = (g.Nx + TX - 1) / TX;
+    const int ntiles = ntx * (A.nrow + A.nrow1);
+    const R dt = (R)A.dt, dx = (R)g.dx, dy = (R)g.dy, idx2 = (R)g.idx2, idy2 = (R)g.idy2;
+    const R cx = dt * idx2, cy = dt * idy2, eps0 = (R)A.eps, lang = (R)A.lang_c;
+    auto tile_of = [&](int q) {
+        const int r = q / ntx;
+        const int by = r < A.nrow ? A.row0 + r : A.row1 + (r - A.nrow);
+        return by * ntx + q % ntx;
+    };
+    auto issue = [&](int q) {                            // thread 0 only
+        const int tile = tile_of(q);
+        const int bx = tile % ntx, by = tile / ntx;
+        const int xg0 = bx * TX - H, prow = g.j0 + by * TYO - K - g.rb;
+        const int xs16 = ((xg0 + 1024) / 16) * 16 - 1024;
+        uint32_t bytes = S::tx_bytes;
+        if (A.same_rhs) bytes -= (uint32_t)(sizeof(C) * EY * TXE);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(t_smem_u32(bar)), "r"(bytes) : "memory");
+        t_tma_load_2d(smem + S::st_psi, &tm_psi, xg0, prow, bar);
+        if (!A.same_rhs) t_tma_load_2d(smem + S::st_rhs, &tm_rhs, xg0, prow, bar);
+        t_tma_load_2d(smem + S::st_a, &tm_a, xg0, prow, bar);
+        t_tma_load_2d(smem + S::st_b, &tm_b, xg0, prow, bar);
+        if (EPS) t_tma_load_2d(smem + S::st_eps, &tm_eps, xg0, prow, bar);
+        t_tma_load_2d(smem + S::st_nf, &tm_nf, xs16, prow, bar);
+    };
+
+    int tile = blockIdx.x;
+    if (A.pdl_trigger == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(t_smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (A.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (tile < ntiles) issue(tile);
+    }
+    {   // all five planes to zero once: the pad entries are never written afterwards
+        C z; z.x = 0; z.y = 0;
+        for (int i = tid; i < 5 * XR * PW; i += NT) pl[i] = z;
+    }
+    __shared__ unsigned int sm_rmax[K];
+    if (tid < K) sm_rmax[tid] = 0u;
+    __shared__ __align__(16) R s_fl[16][4];              // see k_psi_tile
+    if (tid < 16) {
+        const unsigned f = tid;
+        const R nwx = ((f & (NF_MM | NF_MP)) ? (R)1 : (R)0) + ((f & (NF_PM | NF_PP)) ? (R)1 : (R)0);
+        const R nwy = ((f & (NF_MM | NF_PM)) ? (R)1 : (R)0) + ((f & (NF_MP | NF_PP)) ? (R)1 : (R)0);
+        s_fl[f][0] = (f & (NF_PM | NF_PP)) ? cx : (R)0;
+        s_fl[f][1] = (f & (NF_MP | NF_PP)) ? cy : (R)0;
+        s_fl[f][2] = idx2 * nwx + idy2 * nwy;
+        s_fl[f][3] = f ? (R)1 : (R)0;
+    }
+    uint32_t phase = 0;
+
+    for (; tile < ntiles; tile += gridDim.x) {
+        const int tcur = tile_of(tile);
+        const int bx = tcur % ntx, by = tcur / ntx;
+        const int xg0 = bx * TX - H, yg0 = g.j0 + by * TYO - K;
+        const int x0 = xg0 + c0;                          // global column of the patch's even column
+        const int nfd = xg0 - (((xg0 + 1024) / 16) * 16 - 1024);
+        if (tid < 32) {
+            uint32_t ok = 0;
+            while (!ok)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(t_smem_u32(bar)), "r"(phase) : "memory");
+        }
+        phase ^= 1;
+        __syncthreads();      // also: everybody is done with the previous tile's planes
+
+        const bool xin[2] = {x0 >= 0 && x0 < g.Nx, x0 + 1 >= 0 && x0 + 1 < g.Nx};
+        const bool rhs_is_psi = A.same_rhs && !A.noise;
+        if (A.noise) {        // Langevin noise folded into the staged right-hand side (see k_psi_tile)
+#pragma unroll 1
+            for (int n = 0; n < 2 * PR; n++) {
+                const int c = n & 1, r = r0 + (n >> 1), si = r * TXE + c0 + c;
+                C qq = A.same_rhs ? ((const C *)(smem + S::st_psi))[si] : ((const C *)(smem + S::st_rhs))[si];
+                const unsigned f = xin[c] ? (smem + S::st_nf)[r * NFW + nfd + c0 + c] : 0u;
+                if (f) {
+                    uint32_t nn = (uint32_t)(x0 + c) + (uint32_t)g.Nx * (uint32_t)(yg0 + r);
+                    qq.x += lang * (rand_1<R>(nn, A.rand_t) - (R)0.5);
+                    qq.y += lang * (rand_2<R>(nn, A.rand_t) - (R)0.5);
+                }
+                ((C *)(smem + S::st_rhs))[si] = qq;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        // ---- per-node constants into registers
+        C psi[2][PR], q[2][PR], La[2][PR], Lb[2][PR], LbS0[2];
+        R di[2][PR];
+        LbS0[0].x = LbS0[0].y = LbS0[1].x = LbS0[1].y = 0;
+        if (r0 > 0) {         // S-link coefficients of the patch's first row = b-links of tile row r0-1
+            const int si = (r0 - 1) * TXE + c0;
+            const float2 b01 = *(const float2 *)((const R *)(smem + S::st_b) + si);
+            const unsigned f01 = *(const unsigned short *)(smem + S::st_nf + (r0 - 1) * NFW + nfd + c0);
+            const unsigned f0 = xin[0] ? (f01 & 0xffu) : 0u, f1 = xin[1] ? (f01 >> 8) : 0u;
+            R s0, k0, s1, k1;
+            link_sincos2<R, LINKS>(dy * b01.x, dy * b01.y, &s0, &k0, &s1, &k1);
+            const R w0 = s_fl[f0][1], w1 = s_fl[f1][1];
+            LbS0[0].x = w0 * k0; LbS0[0].y = w0 * s0;
+            LbS0[1].x = w1 * k1; LbS0[1].y = w1 * s1;
+        }
+#pragma unroll
+        for (int r = 0; r < PR; r++) {
+            const int row = r0 + r, si = row * TXE + c0;
+            const float4 p01 = *(const float4 *)((const C *)(smem + S::st_psi) + si);
+            const float4 q01 = rhs_is_psi ? p01 : *(const float4 *)((const C *)(smem + S::st_rhs) + si);
+            const float2 a01 = *(const float2 *)((const R *)(smem + S::st_a) + si);
+            const float2 b01 = *(const float2 *)((const R *)(smem + S::st_b) + si);
+            float2 e01;
+            if (EPS) e01 = *(const float2 *)((const R *)(smem + S::st_eps) + si);
+            else { e01.x = eps0; e01.y = eps0; }
+            const unsigned f01 = *(const unsigned short *)(smem + S::st_nf + row * NFW + nfd + c0);
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                C p0, qq;
+                p0.x = c ? p01.z : p01.x; p0.y = c ? p01.w : p01.y;
+                qq.x = c ? q01.z : q01.x; qq.y = c ? q01.w : q01.y;
+                const R av = c ? a01.y : a01.x, bv = c ? b01.y : b01.x, e = c ? e01.y : e01.x;
+                unsigned f = c ? (f01 >> 8) : (f01 & 0xffu);
+                if (!xin[c]) f = 0;
+                const float4 w = *(const float4 *)&s_fl[f][0];
+                const R wE = w.x, wN = w.y, nw = w.z, act = w.w;
+                R sa, ca, sb, cb;
+                C la, lb;
+                link_sincos2<R, LINKS>(dx * av, dy * bv, &sa, &ca, &sb, &cb);
+                la.x = wE * ca; la.y = wE * sa;
+                lb.x = wN * cb; lb.y = wN * sb;
+                qq.x *= act; qq.y *= act;
+                const R D = (R)1.0 + dt * (qq.x * qq.x + qq.y * qq.y - e + nw);
+                const R d = f ? rcp_diag(D) : (R)0;       // inactive / out-of-domain nodes stay exactly 0 (see k_psi_tile)
+                psi[c][r] = p0; q[c][r] = qq; La[c][r] = la; Lb[c][r] = lb; di[c][r] = d;
+            }
+            xe[0][(row + 1) * PW + lane] = psi[0][r];
+            xo[0][(row + 1) * PW + lane + 1] = psi[1][r];
+            slo[(row + 1) * PW + lane + 1] = La[1][r];
+        }
+        __syncthreads();      // staging fully consumed; level-0 values and the odd columns' link coefficients visible
+        if (tid == 0 && tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);
+
+        unsigned inmask = 0;                  // bit c*4 + r: that node of the patch is an output node of the tile
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int r = 0; r < PR; r++)
+                if (c0 + c >= H && c0 + c < TXE - H && x0 + c < g.Nx && r0 + r >= K && r0 + r < EY - K && yg0 + r0 + r < g.j1)
+                    inmask |= 1u << (c * 4 + r);
+
+        // the 16 chained FMAs of k_psi_tile, in its order: W, E, S, N
+        auto node = [&](const C &qv, const C &lw, const C &pw, const C &le, const C &pe, const C &ls, const C &pS, const C &ln,
+                        const C &pN, const R dv) {
+            R ax = qv.x, ay = qv.y;
+            ax = fma_r(lw.x, pw.x, ax);   ay = fma_r(lw.x, pw.y, ay);
+            ax = fma_r(-lw.y, pw.y, ax);  ay = fma_r(lw.y, pw.x, ay);
+            ax = fma_r(le.x, pe.x, ax);   ay = fma_r(le.x, pe.y, ay);
+            ax = fma_r(le.y, pe.y, ax);   ay = fma_r(-le.y, pe.x, ay);
+            ax = fma_r(ls.x, pS.x, ax);   ay = fma_r(ls.x, pS.y, ay);
+            ax = fma_r(-ls.y, pS.y, ax);  ay = fma_r(ls.y, pS.x, ay);
+            ax = fma_r(ln.x, pN.x, ax);   ay = fma_r(ln.x, pN.y, ay);
+            ax = fma_r(ln.y, pN.y, ax);   ay = fma_r(-ln.y, pN.x, ay);
+            C o;
+            o.x = ax * dv; o.y = ay * dv;
+            return o;
+        };
+        auto sweep = [&](const C(&in)[2][PR], C(&out)[2][PR], const int sb, const int k) {
+            const C *se = xe[sb], *so = xo[sb];
+            C *de = xe[sb ^ 1], *dd = xo[sb ^ 1];
+            const C below0 = se[r0 * PW + lane], below1 = so[r0 * PW + lane + 1];                          // tile row r0-1
+            const C above0 = se[(r0 + PR + 1) * PW + lane], above1 = so[(r0 + PR + 1) * PW + lane + 1];   // tile row r0+4
+#pragma unroll
+            for (int r = 0; r < PR; r++) {
+                const int ri = (r0 + r + 1) * PW + lane;
+                const C pw0 = so[ri], lw0 = slo[ri];     // column 2l-1 (index l) and its E-link coefficient
+                const C pe1 = se[ri + 1];                // column 2l+2 (index l+1)
+                out[0][r] = node(q[0][r], lw0, pw0, La[0][r], in[1][r], r > 0 ? Lb[0][r - 1] : LbS0[0],
+                                 r > 0 ? in[0][r - 1] : below0, Lb[0][r], r < PR - 1 ? in[0][r + 1] : above0, di[0][r]);
+                out[1][r] = node(q[1][r], La[0][r], in[0][r], La[1][r], pe1, r > 0 ? Lb[1][r - 1] : LbS0[1],
+                                 r > 0 ? in[1][r - 1] : below1, Lb[1][r], r < PR - 1 ? in[1][r + 1] : above1, di[1][r]);
+            }
+            const bool more = k < K - 1;
+            R rm = 0;
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+#pragma unroll
+                for (int r = 0; r < PR; r++)
+                    if (inmask & (1u << (c * 4 + r)))
+                        rm = fmax(rm, fmax(fabs(out[c][r].x - in[c][r].x), fabs(out[c][r].y - in[c][r].y)));
+            if (more) {
+#pragma unroll
+                for (int r = 0; r < PR; r++) {
+                    const int ri = (r0 + r + 1) * PW + lane;
+                    de[ri] = out[0][r];
+                    dd[ri + 1] = out[1][r];
+                }
+            }
+            const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(rm));
+            if (lane == 0 && wm) atomicMax(&sm_rmax[k], wm);
+            if (more) __syncthreads();
+        };
+        {
+            C nx[2][PR];
+#pragma unroll 1
+            for (int k = 0; k + 1 < K; k += 2) {
+                sweep(psi, nx, 0, k);
+                sweep(nx, psi, 1, k + 1);
+            }
+            if (K & 1) {
+                sweep(psi, nx, 0, K - 1);
+#pragma unroll
+                for (int c = 0; c < 2; c++)
+#pragma unroll
+                    for (int r = 0; r < PR; r++) psi[c][r] = nx[c][r];
+            }
+        }
+        // ---- write the interior
+        {
+            C *o = (C *)A.out + ((long long)(yg0 + r0 - g.rb) * g.P + x0);
+#pragma unroll
+            for (int r = 0; r < PR; r++) {
+                if (inmask & (1u << r)) o[(long long)r * g.P] = psi[0][r];
+                if (inmask & (1u << (4 + r))) o[(long long)r * g.P + 1] = psi[1][r];
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < K) {
+        const double r = (double)__uint_as_float(sm_rmax[tid]);
+        if (r > 0.0) atomicMax(A.slots + tid, (unsigned long long)__double_as_longlong(r));
+    }
+}
+
 // ------------------------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -550,12 +809,22 @@ static int launch_tile_t(svl_ctx *c, TileArgs &A, const TileIO &io) {
     const Geo &g = c->g;
     constexpr int TX = TXE - 2 * S::H, TYO = S::EY - 2 * K;
     static_assert(TYO > 0 && TX > 0, "tile too small for this K");
-    auto kern = k_psi_tile<R, K, TXE, V, NB, EPS, false, LINKS>;
+    typedef void (*kern_t)(TileArgs, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap);
+    kern_t kern = k_psi_tile<R, K, TXE, V, NB, EPS, false, LINKS>;
     auto kern_slab = k_psi_tile<R, K, TXE, V, NB, EPS, true, LINKS>;       // with halo wait + in-kernel push
+    if constexpr (sizeof(R) == 4 && TXE == 64 && V == 8 && NB == 4) {
+        // fp32: the 2 x 4 patch variant for everything but the boundary tile rows of a slab (option psi_patch)
+        static bool patch_ready = false;
+        if (!patch_ready) {
+            SVL_CHECK(cudaFuncSetAttribute(k_psi_patch<K, EPS, LINKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total));
+            patch_ready = true;
+        }
+        if (c->opt_psi_patch) kern = k_psi_patch<K, EPS, LINKS>;
+    }
     static int slots = 0;
     if (!slots) {
         int occ = 1, nsm = 148;
-        SVL_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total));
+        SVL_CHECK(cudaFuncSetAttribute(k_psi_tile<R, K, TXE, V, NB, EPS, false, LINKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total));
         SVL_CHECK(cudaFuncSetAttribute(kern_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total));
         SVL_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern_slab, TXE * NB, S::total));
         SVL_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
