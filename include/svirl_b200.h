@@ -58,8 +58,15 @@ int svl_synchronize(svl_ctx *ctx);
  * "a_kernel" (0 = per-node A sweep, 1..4 = tile kernel fusing sweep pairs in four layouts, default 2),
  * "cg_fused" (2 = two-pass CG iteration svl_cg_pass_a/_b, default where it applies; 1 = three-pass iteration
  * svl_cg_begin/_end; 0 = composition of the single kernels), "spin_timeout_ms" (bound of the spin waits on peer
- * GPUs, 0 = wait forever, default; env SVL_SPIN_TIMEOUT_MS) */
+ * GPUs, 0 = wait forever, default; env SVL_SPIN_TIMEOUT_MS); round 2b: "psi_links" (fp32 tile kernel: 1 = MUFU link
+ * variables, default; 0 = polynomial sincos), "psi_patch" (1 = 2x4 node patch per thread, default; 0 = 1x8 column),
+ * "psi_shape", "pipeline" (kappa = inf svl_td_run: next step's first launch pre-issued behind a device-side stop rule),
+ * "pdl" (programmatic dependent launches: 0 off, 1 one GPU, 2 also slab batches, default), "slab_split", "slab_bnd"
+ * (CTAs of the boundary launch of a slab batch: 0 = svl_slab_split_plan); the full table is in INTEGRATION.md section 6 */
 int svl_set_option(svl_ctx *ctx, const char *name, int value);
+/* host arithmetic behind option "slab_bnd" = 0: CTAs given to the nb boundary tiles of a slab batch when ni interior
+ * tiles share `slots` resident CTAs (new; the reference is single-GPU) */
+int svl_slab_split_plan(int nb, int ni, int slots);
 int svl_get_stat(svl_ctx *ctx, const char *name, double *value);
 /* self-test hook: the library's own sincos (used for every link variable exp(-i d A)) on n values */
 int svl_debug_sincos(svl_ctx *ctx, size_t n, const double *x, double *s_out, double *c_out);

@@ -22,6 +22,7 @@ SIGNATURES = {
     "svl_synchronize": ([_p], _i),
     "svl_set_option": ([_p, C.c_char_p, _i], _i),
     "svl_get_stat": ([_p, C.c_char_p, _pd], _i),
+    "svl_slab_split_plan": ([_i, _i, _i], _i),
     "svl_debug_sincos": ([_p, _sz, _pd, _pd, _pd], _i),
     "svl_debug_trace": ([_p, C.POINTER(C.c_ulonglong), _i, C.POINTER(_i)], _i),
     "svl_event_record": ([_p, _i], _i),

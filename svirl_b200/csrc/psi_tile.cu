@@ -763,6 +763,25 @@ static int t_make_map(CUtensorMap *tm, CUtensorMapDataType dt, const void *base,
     return 0;
 }
 
+// CTAs of the boundary launch of a slab batch: nb boundary tiles, ni interior tiles, `slots` resident CTAs per GPU.
+// Boundary CTAs need ceil(nb / t) tile times plus ~3 for their one system-scope fence, the interior ones
+// ceil(ni / (slots - t)); the boundary CTAs should be done well before the interior ones (their tiles wait for halo
+// flags and the fence time is only roughly known), so a boundary time above 0.85 of the interior time counts as the
+// batch time with that margin.  Smallest batch time wins, ties go to the faster boundary.  Pure host arithmetic
+// (tests/test_slab_host.py).
+extern "C" int svl_slab_split_plan(int nb, int ni, int slots) {
+    if (nb <= 0 || slots <= 1) return nb < 1 ? 1 : (nb < slots ? nb : slots);
+    long best = -1, best_b = 0;
+    int best_t = nb < slots ? nb : slots;
+    const int tmax = nb < slots / 2 ? nb : slots / 2;
+    for (int t = 1; t <= tmax; t++) {
+        const long rb = (nb + t - 1) / t + 3, ri = ((long)ni + (slots - t) - 1) / (slots - t);
+        const long r = 20 * rb > 17 * ri ? (rb * 20 + 16) / 17 : ri;
+        if (best < 0 || r < best || (r == best && rb < best_b)) { best = r; best_b = rb; best_t = t; }
+    }
+    return best_t;
+}
+
 struct TileIO {
     const void *psi, *rhs, *a, *b, *epsf;
     const uint8_t *nf;
@@ -891,19 +910,7 @@ static int launch_tile_t(svl_ctx *c, TileArgs &A, const TileIO &io) {
         // 11 rounds like a single GPU, 15 would push it to 12), so the split is chosen by evaluating that maximum.
         int gb = nb < slots ? nb : slots;
         if (c->opt_slab_bnd > 0) gb = c->opt_slab_bnd < gb ? c->opt_slab_bnd : gb;
-        else if (c->opt_slab_bnd == 0) {
-            long best = -1, best_b = 0;
-            int best_t = gb;
-            const int tmax = nb < slots / 2 ? nb : slots / 2;
-            for (int t = 1; t <= tmax; t++) {
-                const long rb = (nb + t - 1) / t + 3, ri = ((long)ni + (slots - t) - 1) / (slots - t);
-                // the boundary CTAs should be done well before the interior ones: their tiles wait for halo flags and
-                // their fence time is only roughly known
-                const long r = 20 * rb > 17 * ri ? (rb * 20 + 16) / 17 : ri;
-                if (best < 0 || r < best || (r == best && rb < best_b)) { best = r; best_b = rb; best_t = t; }
-            }
-            gb = best_t;
-        }
+        else if (c->opt_slab_bnd == 0) gb = svl_slab_split_plan(nb, ni, slots);
         B.defer_publish = 1;
         const bool chain = c->opt_pdl >= 2 && !A.gate;
         if (chain) {

@@ -62,3 +62,35 @@ def test_max_reduce_and_handle_exchange_world2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_slab_split_plan_keeps_the_interior_at_single_gpu_rounds():
+    """svl_slab_split_plan (host arithmetic behind option slab_bnd = 0): how many CTAs the boundary tile rows of a slab
+    batch get.  For the weak-scaling workload (2048 x 2048 nodes per GPU, 56 x 24 output tiles, 296 resident CTAs) the
+    interior launch must still finish in the 11 rounds a single GPU needs, and the boundary CTAs (tiles + 3 tile times
+    of fence) well before it; the call must be safe for degenerate sizes."""
+    from svirl_b200 import _lib
+    lib = _lib.load()
+    plan = lib.svl_slab_split_plan
+
+    def rounds(nb, ni, slots, t):
+        return -(-nb // t) + 3, -(-ni // (slots - t))
+
+    ntx, nty, slots = 37, 86, 296
+    assert -(-ntx * nty // slots) == 11                       # one GPU: 3182 tiles on 296 CTAs
+    for nbrows in (1, 2):                                      # one neighbour (end ranks) / two neighbours
+        nb, ni = ntx * nbrows, ntx * (nty - nbrows)
+        t = plan(nb, ni, slots)
+        rb, ri = rounds(nb, ni, slots, t)
+        assert 1 <= t <= nb and ri == 11 and rb <= 0.85 * ri, (nbrows, t, rb, ri)
+        # no other split is better
+        for u in range(1, min(nb, slots // 2) + 1):
+            ub, ui = rounds(nb, ni, slots, u)
+            cost = lambda b, i: i if 20 * b <= 17 * i else (20 * b + 16) // 17      # noqa: E731
+            assert cost(rb, ri) <= cost(ub, ui)
+    # strong scaling of 32768^2 fp64 on 8 GPUs: 586 tiles per tile row, 148 resident CTAs
+    t = plan(2 * 586, 170 * 586, 148)
+    rb, ri = rounds(2 * 586, 170 * 586, 148, t)
+    assert rb <= 0.85 * ri and ri <= 1.02 * (172 * 586 / 148)
+    # degenerate sizes
+    assert plan(0, 10, 296) >= 1 and plan(5, 0, 296) >= 1 and plan(3, 3, 2) >= 1 and plan(12, 18, 296) <= 12
