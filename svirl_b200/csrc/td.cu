@@ -500,6 +500,7 @@ extern "C" int svl_td_psi_solve(svl_ctx *c, double dt, double eps, const svl_buf
                                 svl_buf *psi, double lang_c, uint32_t rand_t, double stop_eps, int *sweeps_out) {
     SVL_REQUIRE(c, "null context");
     SVL_TRY(check_kinds(psi, ab, epsf));
+    c->spec_issued = 0;                              // a stand-alone solve never continues a pre-issued launch
     return psi_solve(c, dt, eps, epsf, ab, psi, lang_c, rand_t, stop_eps, sweeps_out, nullptr);
 }
 
