@@ -219,3 +219,29 @@ def test_pipelined_solves_equal_plain_solves_bitwise(dtype):
         assert out[0][1] == out[1][1], (lang, out[0][1], out[1][1])
         assert np.array_equal(out[0][0], out[1][0]), lang
         assert out[0][2] == 0 and out[1][2] > 0, (lang, out[0][2:], out[1][2:])
+
+
+@pytest.mark.parametrize("shape", [(300, 270), (131, 71)], ids=["multi_tile", "ragged"])
+@pytest.mark.parametrize("epsfield", [False, True], ids=["eps_scalar", "eps_field"])
+def test_patch_kernel_equals_column_kernel_bitwise(shape, epsfield):
+    """k_psi_patch (2 x 4 nodes per thread, option psi_patch = 1, default) performs the column kernel's 16-FMA chain per
+    node in the same order: fp32 psi and sweep counts are bit-identical with psi_patch = 0, with a spatially varying
+    linear coefficient, holes, Langevin noise and grids that end inside a tile."""
+    from svirl_b200 import GLSolver
+    Nx, Ny = shape
+    rs = np.random.RandomState(11)
+    mt = rs.rand(Nx - 1, Ny - 1) > 0.08
+    out = []
+    for patch in (1, 0):
+        kw = dict(Nx=Nx, Ny=Ny, dx=0.5, dy=0.4, dtype=np.float32, gl_parameter=np.inf, homogeneous_external_field=0.15,
+                  random_seed=9, material_tiling=mt, order_parameter_Langevin_coefficient=0.03)
+        if epsfield:
+            kw["linear_coefficient"] = (0.6 + 0.4 * np.random.RandomState(5).rand(Nx, Ny)).astype(np.float32)
+        gl = GLSolver(**kw)
+        gl.par.set_option("graphs", 0)
+        gl.par.set_option("psi_patch", patch)
+        gl.solve.td(dt=0.1, Nt=7)
+        out.append((gl.flatten_array(gl.vars.order_parameter).copy(), gl.solve._td.sweeps_order_parameter))
+        gl.par.close()
+    assert out[0][1] == out[1][1]
+    assert np.isfinite(out[0][0]).all() and np.array_equal(out[0][0], out[1][0])
