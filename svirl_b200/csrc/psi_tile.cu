@@ -4,15 +4,21 @@
 //   * a CTA loads an extended tile of TXE x EY nodes (interior + halo of H = roundup(K,4)
 //     columns / K rows) with one set of 2-D TMA boxes (psi, rhs, a, b, [eps], flags) into shared
 //     memory; zero fill outside the plane supplies the domain boundary;
-//   * each thread owns V consecutive rows of one column for all K sweeps.  Everything that is
-//     constant during the solve -- right-hand side, 1/diagonal and the two link coefficients
-//     w*dt/d^2*exp(-i d A) of its nodes (one sincos per link and launch) -- lives in REGISTERS;
-//     only the psi iterate goes through shared memory (double buffered, one __syncthreads per
-//     sweep), and only the W/E neighbours (+ the two strip ends) are read from it: about 3 shared
-//     loads and 1 shared store per node update instead of 11 + 1 in the streaming variant;
+//   * everything that is constant during the solve -- right-hand side, 1/diagonal and the two link
+//     coefficients w*dt/d^2*exp(-i d A) of a thread's nodes (one sincos per link and launch; fp32: MUFU after an
+//     exact reduction, link_sincos) -- lives in REGISTERS; the material flags of a node index a 16-entry shared
+//     table of link weights / neighbour term / activity; only the psi iterate goes through shared memory (double
+//     buffered, one __syncthreads per sweep);
+//   * k_psi_tile: a thread owns V consecutive rows of ONE COLUMN (26 shared loads + 8 stores per sweep for 8
+//     nodes); k_psi_patch (fp32, everything but the boundary tile rows of a slab): a thread owns a PATCH of
+//     2 columns x 4 rows with the iterate in separate planes for the even and the odd columns (16 + 8).  Both do
+//     the same 16 chained FMAs per node in the same order: bit-identical results;
 //   * the halo shrinks by one ring per sweep; after K sweeps the interior is exact and is
 //     written back; the max-norm update of each of the K sweeps is reduced over the interior
-//     and merged with one atomicMax per CTA and sweep.
+//     (REDUX per warp, shared atomicMax) and merged with one global atomicMax per CTA and sweep;
+//   * launches of one solve are chained as programmatic dependent launches (griddepcontrol); a launch issued ahead
+//     of the host's stop decision carries a gate word (td.cu: pipelined solves); on row slabs the boundary tile
+//     rows run in a launch of their own on a few CTAs (halo-flag wait, peer stores, one fence per CTA).
 // HBM traffic per launch: the one-sweep bytes times the halo overhead (1.3-1.5x), for K sweeps.
 #include "common.cuh"
 #include <cuda.h>
